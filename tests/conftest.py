@@ -1,0 +1,32 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: test needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    return np.load(os.path.join(GOLDEN_DIR, "golden.npz"))
+
+
+@pytest.fixture(scope="session")
+def golden_levels():
+    with open(os.path.join(GOLDEN_DIR, "levels.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_cases():
+    with open(os.path.join(GOLDEN_DIR, "env_cases.json")) as f:
+        return json.load(f)
