@@ -1,0 +1,107 @@
+"""ctypes binding of libgu_b200.so (the C ABI declared in include/gu_b200.h).
+
+There is no CPU fallback: if the library has not been built, or a call returns a
+non-zero code, this module raises.  Only raw device pointers, sizes and a stream
+handle cross the boundary; PyTorch owns every buffer.
+"""
+import ctypes
+import os
+
+from . import build as _build
+
+c_i32p = ctypes.c_void_p
+c_ptr = ctypes.c_void_p
+
+GU_FLAG_AUTO_RESET = 1
+GU_FLAG_NO_CARE_TERMINAL = 2
+GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
+
+EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
+           "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_vi_small_f64",
+           "gu_vi_small_max_cells", "gu_version", "gu_arch", "gu_error_string")
+
+
+class GuLevels(ctypes.Structure):
+    """struct gu_levels (include/gu_b200.h)."""
+    _fields_ = [("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("per_env", ctypes.c_int32),
+                ("words", ctypes.c_int32), ("wall", c_ptr), ("goal", c_ptr), ("lava", c_ptr),
+                ("start", c_ptr)]
+
+
+class GuGrid(ctypes.Structure):
+    """struct gu_grid (include/gu_b200.h)."""
+    _fields_ = [("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("row_begin", ctypes.c_int32),
+                ("row_end", ctypes.c_int32), ("pitch", ctypes.c_int32), ("pitch_words", ctypes.c_int32),
+                ("wall", c_ptr), ("goal", c_ptr), ("lava", c_ptr)]
+
+
+class GuError(RuntimeError):
+    def __init__(self, fn, code, msg):
+        RuntimeError.__init__(self, "%s failed with code %d: %s" % (fn, code, msg))
+        self.code = code
+
+
+_LIB = None
+
+
+def library_path():
+    return _build.LIB_PATH
+
+
+def lib():
+    """Load (once) and return the shared library; raise loudly if it is missing."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise RuntimeError(
+            "libgu_b200.so is not built (%s). Build it with `python -m griduniverse_b200.build` "
+            "or `python -c 'import __graft_entry__ as g; g.build()'`. There is no CPU fallback." % path)
+    L = ctypes.CDLL(path)
+    i32, i64, u32, f32, f64, p = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_float,
+                                  ctypes.c_double, c_ptr)
+    lvp, gp = ctypes.POINTER(GuLevels), ctypes.POINTER(GuGrid)
+    sig = {
+        "gu_step": (ctypes.c_int, [lvp, i64, p, p, p, p, p, p, p, u32, p]),
+        "gu_rollout": (ctypes.c_int, [lvp, i64, i64, p, p, p, p, p, p, p, p, p, p, u32, p]),
+        "gu_rollout_policy": (ctypes.c_int, [lvp, i64, i64, p, p, p, p, p, p, p, p]),
+        "gu_mc_episode_f64": (ctypes.c_int, [i32, i32, p, p, p, i64, p, p, i32, i32, f64, p, p, p, p, p]),
+        "gu_mc_finalize_f64": (ctypes.c_int, [i32, p, p, p, p]),
+        "gu_synth_env_levels": (ctypes.c_int, [i32, i32, i64, i64, u32, p, p, p, p, p]),
+        "gu_synth_maze": (ctypes.c_int, [i32, i32, i32, i32, i32, u32, p, p, p, p]),
+        "gu_tables_bytes": (i64, [lvp, i64]),
+        "gu_pack_tables": (ctypes.c_int, [lvp, i64, p, u32, p]),
+        "gu_look_step_ahead": (ctypes.c_int, [lvp, i64, p, p, p, p, p, u32, p]),
+        "gu_sweep_f64": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f64, p, p, f64, p]),
+        "gu_sweep_f32": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f32, p, p, f32, p]),
+        "gu_greedy_f64": (ctypes.c_int, [gp, p, p, f64, p]),
+        "gu_greedy_f32": (ctypes.c_int, [gp, p, p, f32, p]),
+        "gu_vi_small_f64": (ctypes.c_int, [gp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),
+        "gu_vi_small_max_cells": (i64, []),
+        "gu_version": (ctypes.c_int, []),
+        "gu_arch": (ctypes.c_char_p, []),
+        "gu_error_string": (ctypes.c_char_p, [ctypes.c_int]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)   # AttributeError here = the library does not export the header's symbol
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = L
+    return L
+
+
+def check(fn_name, code):
+    if code != 0:
+        raise GuError(fn_name, code, lib().gu_error_string(code).decode())
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    import torch
+    s = torch.cuda.current_stream() if stream is None else stream
+    return ctypes.c_void_p(s.cuda_stream)

@@ -1,0 +1,293 @@
+// gu_env.cu -- batched GridUniverseEnv.step / look_step_ahead / rollouts (sm_100a).
+//
+// Reference: core/envs/griduniverse_env.py:51-54 (edge-clamped moves), :136-155
+// (look_step_ahead), :157-174 (wall / terminal predicates), :176-193 (_step / _reset).
+// One thread owns one env (four consecutive envs in the vectorised variants, so that
+// positions, actions and outputs move as coalesced 16-byte requests).
+#include "gu_common.cuh"
+
+namespace gu {
+
+struct LevelsView {
+  int X, Y, per_env, words;
+  const uint32_t* wall;
+  const uint32_t* goal;
+  const uint32_t* lava;
+  const int32_t* start;
+  int64_t N;
+};
+
+static inline LevelsView view_of(const gu_levels* lv, int64_t n) {
+  LevelsView v;
+  v.X = lv->X; v.Y = lv->Y; v.per_env = lv->per_env; v.words = lv->words;
+  v.wall = lv->wall; v.goal = lv->goal; v.lava = lv->lava; v.start = lv->start; v.N = n;
+  return v;
+}
+
+static int check_levels(const gu_levels* lv, int64_t n) {
+  if (!lv || !lv->wall || !lv->goal || !lv->lava) return GU_ERR_NULL;
+  if (lv->X <= 0 || lv->Y <= 0 || n < 0) return GU_ERR_SHAPE;
+  const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
+  if (cells > (1ll << 30) || lv->words != static_cast<int32_t>((cells + 31) / 32)) return GU_ERR_SHAPE;
+  return GU_OK;
+}
+
+__device__ __forceinline__ bool plane_bit(const uint32_t* __restrict__ plane, const LevelsView& lv,
+                                          int64_t env, int s) {
+  const int64_t idx = lv.per_env ? static_cast<int64_t>(s >> 5) * lv.N + env : (s >> 5);
+  return (__ldg(plane + idx) >> (s & 31)) & 1u;
+}
+
+// The four lambdas at griduniverse_env.py:51-54.  Only the two low bits of the action are
+// used, so -1..-4 behave like the reference's negative list index (LEFT..UP).
+__device__ __forceinline__ int clamp_move(int s, int a, int X, int Y) {
+  const int y = s / X, x = s - y * X;
+  switch (a & 3) {
+    case 0: return y > 0 ? s - X : s;
+    case 1: return x < X - 1 ? s + 1 : s;
+    case 2: return y < Y - 1 ? s + X : s;
+    default: return x > 0 ? s - 1 : s;
+  }
+}
+
+// look_step_ahead (griduniverse_env.py:136-155)
+__device__ __forceinline__ void transition(const LevelsView& lv, int64_t env, int s, int a, bool care,
+                                           int& n, int& r, bool& term) {
+  n = s;
+  const bool stay = care && (plane_bit(lv.goal, lv, env, s) || plane_bit(lv.lava, lv, env, s));
+  if (!stay) {
+    const int c = clamp_move(s, a, lv.X, lv.Y);
+    if (!plane_bit(lv.wall, lv, env, c)) n = c;
+  }
+  const bool g = plane_bit(lv.goal, lv, env, n), l = plane_bit(lv.lava, lv, env, n);
+  r = reward_of(g, l);
+  term = g | l;
+}
+
+__device__ __forceinline__ int start_of(const LevelsView& lv, int64_t env) {
+  return __ldg(lv.start + (lv.per_env ? env : 0));
+}
+
+// Warp-reduce the per-thread counters and publish them with one atomic pair per warp.
+__device__ __forceinline__ void publish_stats(long long rsum, long long dcnt, int64_t* stats) {
+  if (stats == nullptr) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (rsum != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats), static_cast<unsigned long long>(rsum));
+    if (dcnt != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), static_cast<unsigned long long>(dcnt));
+  }
+}
+
+// ---- one step per launch ("gym mode") ---------------------------------------------------
+// VEC = 4: each thread moves four consecutive envs with int4 / uchar4 requests.
+template <int VEC>
+__global__ void __launch_bounds__(256)
+step_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+            int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+            const int32_t* __restrict__ start_choice, int64_t* stats, uint32_t flags) {
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * VEC;
+  const bool care = !(flags & GU_FLAG_NO_CARE_TERMINAL);
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  long long rsum = 0, dcnt = 0;
+  if (i0 < lv.N) {
+    int a[VEC], s[VEC], n[VEC], r[VEC], nxt[VEC];
+    bool d[VEC];
+    if (VEC == 4) {
+      const int4 av = *reinterpret_cast<const int4*>(actions + i0);
+      const int4 sv = *reinterpret_cast<const int4*>(pos + i0);
+      a[0] = av.x; a[1] = av.y; a[2] = av.z; a[3] = av.w;
+      s[0] = sv.x; s[1] = sv.y; s[2] = sv.z; s[3] = sv.w;
+    } else {
+      a[0] = actions[i0];
+      s[0] = pos[i0];
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      transition(lv, i0 + k, s[k], a[k], care, n[k], r[k], d[k]);
+      nxt[k] = n[k];
+      if (auto_reset && d[k]) nxt[k] = start_choice ? __ldg(start_choice + i0 + k) : start_of(lv, i0 + k);
+      rsum += r[k];
+      dcnt += d[k] ? 1 : 0;
+    }
+    if (VEC == 4) {
+      *reinterpret_cast<int4*>(pos + i0) = make_int4(nxt[0], nxt[1], nxt[2], nxt[3]);
+      if (obs) *reinterpret_cast<int4*>(obs + i0) = make_int4(n[0], n[1], n[2], n[3]);
+      if (reward) *reinterpret_cast<int4*>(reward + i0) = make_int4(r[0], r[1], r[2], r[3]);
+      if (done) *reinterpret_cast<uchar4*>(done + i0) = make_uchar4(d[0], d[1], d[2], d[3]);
+    } else {
+      pos[i0] = nxt[0];
+      if (obs) obs[i0] = n[0];
+      if (reward) reward[i0] = r[0];
+      if (done) done[i0] = d[0];
+    }
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
+// ---- T steps per launch, layout-agnostic version ------------------------------------------
+// One thread per env, position in a register, actions[t][n] read coalesced across the warp.
+__global__ void __launch_bounds__(256)
+rollout_generic_kernel(LevelsView lv, int64_t T, const int32_t* __restrict__ actions,
+                       int32_t* __restrict__ pos, int32_t* __restrict__ obs,
+                       int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                       const int32_t* __restrict__ start_choice, int32_t* __restrict__ env_return,
+                       int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const bool care = !(flags & GU_FLAG_NO_CARE_TERMINAL);
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  long long rsum = 0, dcnt = 0;
+  if (i < lv.N) {
+    int s = pos[i];
+    const int st = start_of(lv, i);
+    for (int64_t t = 0; t < T; ++t) {
+      const int64_t o = t * lv.N + i;
+      int n, r;
+      bool d;
+      transition(lv, i, s, __ldg(actions + o), care, n, r, d);
+      if (obs) obs[o] = n;
+      if (reward) reward[o] = r;
+      if (done) done[o] = d;
+      s = n;
+      if (auto_reset && d) s = start_choice ? __ldg(start_choice + o) : st;
+      rsum += r;
+      dcnt += d ? 1 : 0;
+    }
+    pos[i] = s;
+    if (env_return) env_return[i] = static_cast<int32_t>(rsum);
+    if (env_done) env_done[i] = static_cast<int32_t>(dcnt);
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
+__global__ void __launch_bounds__(256)
+look_kernel(LevelsView lv, int64_t m, const int32_t* __restrict__ states,
+            const int32_t* __restrict__ actions, int32_t* __restrict__ next,
+            int32_t* __restrict__ reward, uint8_t* __restrict__ terminal, uint32_t flags) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= m) return;
+  int n, r;
+  bool d;
+  transition(lv, i, states[i], actions[i], !(flags & GU_FLAG_NO_CARE_TERMINAL), n, r, d);
+  if (next) next[i] = n;
+  if (reward) reward[i] = r;
+  if (terminal) terminal[i] = d;
+}
+
+// Policy-driven episodes (monte_carlo.py:7-26): one thread per episode, shared level.
+__global__ void __launch_bounds__(256)
+rollout_policy_kernel(LevelsView lv, int64_t T, const double* __restrict__ cdf,
+                      const double* __restrict__ uniforms, int32_t* __restrict__ pos,
+                      int32_t* __restrict__ obs, int32_t* __restrict__ reward,
+                      int32_t* __restrict__ length, uint8_t* __restrict__ done) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= lv.N) return;
+  int s = pos[i];
+  bool d = false;
+  int64_t t = 0;
+  for (; t < T && !d; ++t) {
+    const int64_t o = t * lv.N + i;
+    const double u = __ldg(uniforms + o);
+    const double* row = cdf + static_cast<int64_t>(s) * 4;
+    // searchsorted(cdf, u, side='right'): number of entries <= u (cdf[3] == 1 > u)
+    int a = (__ldg(row) <= u) + (__ldg(row + 1) <= u) + (__ldg(row + 2) <= u);
+    int n, r;
+    transition(lv, i, s, a, true, n, r, d);
+    if (obs) obs[o] = n;
+    if (reward) reward[o] = r;
+    s = n;
+  }
+  pos[i] = s;
+  if (length) length[i] = static_cast<int32_t>(t);
+  if (done) done[i] = d;
+}
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool aligned4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+// Table-driven fast paths (gu_env_tables.cu).
+int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos,
+                   int32_t* obs, int32_t* reward, uint8_t* done, const int32_t* start_choice,
+                   int32_t* env_return, int32_t* env_done, int64_t* stats, const uint32_t* tables,
+                   uint32_t flags, cudaStream_t st);
+
+}  // namespace gu
+
+using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* lv, int64_t n, const int32_t* actions, int32_t* pos, int32_t* obs,
+                       int32_t* reward, uint8_t* done, const int32_t* start_choice, int64_t* stats,
+                       uint32_t flags, void* stream) {
+  int rc = check_levels(lv, n);
+  if (rc) return rc;
+  if (!actions || !pos) return GU_ERR_NULL;
+  if ((flags & GU_FLAG_AUTO_RESET) && !start_choice && !lv->start) return GU_ERR_NULL;
+  if (n == 0) return GU_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const LevelsView v = view_of(lv, n);
+  const bool vec = (n % 4 == 0) && aligned16(actions) && aligned16(pos) && (!obs || aligned16(obs)) &&
+                   (!reward || aligned16(reward)) && (!done || aligned4(done));
+  if (vec) {
+    const int64_t threads = n / 4;
+    step_kernel<4><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
+        v, actions, pos, obs, reward, done, start_choice, stats, flags);
+  } else {
+    step_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+        v, actions, pos, obs, reward, done, start_choice, stats, flags);
+  }
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_rollout(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos,
+                          int32_t* obs, int32_t* reward, uint8_t* done, const int32_t* start_choice,
+                          int32_t* env_return, int32_t* env_done, int64_t* stats, const uint32_t* tables,
+                          uint32_t flags, void* stream) {
+  int rc = check_levels(lv, n);
+  if (rc) return rc;
+  if (!actions || !pos) return GU_ERR_NULL;
+  if (T < 0) return GU_ERR_SHAPE;
+  if ((flags & GU_FLAG_AUTO_RESET) && !start_choice && !lv->start) return GU_ERR_NULL;
+  if (n == 0 || T == 0) return GU_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (tables) {
+    rc = rollout_tables(lv, n, T, actions, pos, obs, reward, done, start_choice, env_return, env_done,
+                        stats, tables, flags, st);
+    if (rc != GU_ERR_UNSUPPORTED) return rc;
+  }
+  rollout_generic_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
+      view_of(lv, n), T, actions, pos, obs, reward, done, start_choice, env_return, env_done, stats, flags);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_rollout_policy(
+    const gu_levels* lv, int64_t n, int64_t T, const double* cdf, const double* uniforms, int32_t* pos,
+    int32_t* obs, int32_t* reward, int32_t* length, uint8_t* done, void* stream) {
+  int rc = check_levels(lv, n);
+  if (rc) return rc;
+  if (!cdf || !uniforms || !pos) return GU_ERR_NULL;
+  if (lv->per_env) return GU_ERR_UNSUPPORTED;
+  if (T < 0) return GU_ERR_SHAPE;
+  if (n == 0) return GU_OK;
+  rollout_policy_kernel<<<static_cast<unsigned>((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      view_of(lv, n), T, cdf, uniforms, pos, obs, reward, length, done);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_look_step_ahead(const gu_levels* lv, int64_t m, const int32_t* states,
+                                  const int32_t* actions, int32_t* next, int32_t* reward,
+                                  uint8_t* terminal, uint32_t flags, void* stream) {
+  int rc = check_levels(lv, m);
+  if (rc) return rc;
+  if (!states || !actions) return GU_ERR_NULL;
+  if (m == 0) return GU_OK;
+  look_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      view_of(lv, m), m, states, actions, next, reward, terminal, flags);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

@@ -1,0 +1,104 @@
+// gu_mc.cu -- Monte-Carlo evaluation: per-episode truncated discounted returns, first /
+// every-visit accumulation and the value update (core/algorithms/monte_carlo.py:53-97).
+//
+// The reference sums  G(idx) = sum_i gamma^i * r[idx+i]  over the i with gamma^i > threshold,
+// left to right, for every counted visit index, then folds the per-state sums into V
+// sequentially over episodes.  To stay bit-exact the device keeps exactly that order:
+// one thread per visit index for G (sequential in i), one thread per state for the
+// accumulation over visit indices (sequential in idx).  fp64, no fused multiply-add.
+#include "gu_common.cuh"
+
+namespace gu {
+
+__device__ __forceinline__ int mc_state(int start, const int32_t* __restrict__ obs, int64_t stride, int idx) {
+  return idx == 0 ? start : __ldg(obs + static_cast<int64_t>(idx - 1) * stride);
+}
+
+// G[idx], idx in [0, L]  (monte_carlo.py:69-70; an empty tail gives 0)
+__global__ void __launch_bounds__(128)
+mc_returns_kernel(int L, const int32_t* __restrict__ rewards, int64_t stride,
+                  const double* __restrict__ weights, const uint8_t* __restrict__ keep,
+                  double* __restrict__ G) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx > L) return;
+  double acc = 0.0;
+  const int n = L - idx;
+  for (int i = 0; i < n; ++i) {
+    if (__ldg(keep + i)) {
+      const double r = static_cast<double>(__ldg(rewards + static_cast<int64_t>(idx + i) * stride));
+      acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + i), r));
+    }
+  }
+  G[idx] = acc;
+}
+
+// per state: visit counting (:56-68), return accumulation (:71) and the update (:74-91)
+__global__ void __launch_bounds__(128)
+mc_update_kernel(int cells, int L, const int32_t* __restrict__ start_p, const int32_t* __restrict__ obs,
+                 int64_t stride, const double* __restrict__ G, int every_visit, int mode, double alpha,
+                 double* __restrict__ total_visits, double* __restrict__ total_return,
+                 double* __restrict__ value) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cells) return;
+  const int start = __ldg(start_p);
+  double visits = 0.0, ret = 0.0;
+  for (int idx = 0; idx <= L; ++idx) {
+    if (mc_state(start, obs, stride, idx) != s) continue;
+    if (visits != 0.0 && !every_visit) continue;
+    visits = __dadd_rn(visits, 1.0);
+    ret = __dadd_rn(ret, G[idx]);
+  }
+  const double tv = __dadd_rn(total_visits[s], visits);
+  total_visits[s] = tv;
+  if (mode == 2) {                       // not incremental_mean: S(s) += G (:78-80)
+    total_return[s] = __dadd_rn(total_return[s], ret);
+  } else if (mode == 0) {                // V += (1/N) * (G - V) for every state with N > 0 (:83-87)
+    if (tv > 0.0) {
+      const double v = value[s];
+      value[s] = __dadd_rn(v, __dmul_rn(__ddiv_rn(1.0, tv), __dadd_rn(ret, -v)));
+    }
+  } else {                               // non-stationary: V += alpha * (G - V) (:88-91)
+    const double v = value[s];
+    value[s] = __dadd_rn(v, __dmul_rn(alpha, __dadd_rn(ret, -v)));
+  }
+}
+
+__global__ void __launch_bounds__(128)
+mc_finalize_kernel(int cells, const double* __restrict__ total_visits,
+                   const double* __restrict__ total_return, double* __restrict__ value) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= cells) return;
+  if (total_visits[s] > 0.0) value[s] = __ddiv_rn(total_return[s], total_visits[s]);   // :93-97
+}
+
+}  // namespace gu
+
+using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_mc_episode_f64(
+    int32_t cells, int32_t episode_len, const int32_t* start, const int32_t* obs,
+    const int32_t* rewards, int64_t stride, const double* weights, const uint8_t* keep, int32_t every_visit,
+    int32_t mode, double alpha, double* g_scratch, double* total_visits, double* total_return, double* value,
+    void* stream) {
+  if (!start || !obs || !rewards || !weights || !keep || !g_scratch || !total_visits || !total_return || !value)
+    return GU_ERR_NULL;
+  if (cells <= 0 || episode_len < 0 || stride <= 0 || mode < 0 || mode > 2) return GU_ERR_SHAPE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int L = episode_len;
+  mc_returns_kernel<<<(L + 1 + 127) / 128, 128, 0, st>>>(L, rewards, stride, weights, keep, g_scratch);
+  GU_CHECK_LAUNCH();
+  mc_update_kernel<<<(cells + 127) / 128, 128, 0, st>>>(cells, L, start, obs, stride, g_scratch, every_visit,
+                                                         mode, alpha, total_visits, total_return, value);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_mc_finalize_f64(
+    int32_t cells, const double* total_visits, const double* total_return, double* value, void* stream) {
+  if (!total_visits || !total_return || !value) return GU_ERR_NULL;
+  if (cells <= 0) return GU_ERR_SHAPE;
+  mc_finalize_kernel<<<(cells + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+      cells, total_visits, total_return, value);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

@@ -1,0 +1,277 @@
+// gu_plan.cu -- Bellman sweep, greedy extraction and the single-block VI loop (sm_100a).
+//
+// Reference: core/algorithms/utils.py:15-27,55-72 and dynamic_programming.py:8-28.
+// This file holds the layout-agnostic kernels (any X / pitch); the TMA-tiled kernels for
+// large aligned grids live in gu_plan_tiled.cu and share gu_cell.cuh's arithmetic.
+#include "gu_cell.cuh"
+
+namespace gu {
+
+static inline GridView view_of(const gu_grid* g) {
+  GridView v;
+  v.X = g->X; v.Y = g->Y; v.row_begin = g->row_begin; v.row_end = g->row_end;
+  v.pitch = g->pitch; v.pitch_words = g->pitch_words;
+  v.wall = g->wall; v.goal = g->goal; v.lava = g->lava;
+  return v;
+}
+
+int check_grid(const gu_grid* g) {
+  if (!g || !g->wall || !g->goal || !g->lava) return GU_ERR_NULL;
+  if (g->X <= 0 || g->Y <= 0 || g->row_begin < 0 || g->row_end > g->Y || g->row_begin >= g->row_end)
+    return GU_ERR_SHAPE;
+  if (g->pitch < g->X || g->pitch_words * 32 < g->X) return GU_ERR_SHAPE;
+  return GU_OK;
+}
+
+// ---- generic sweep: one thread per cell, 32x8 cells per block -----------------------
+template <typename T, int KIND>
+__global__ void __launch_bounds__(256)
+sweep_generic_kernel(GridView g, const T* __restrict__ vin, T* __restrict__ vout,
+                     const void* __restrict__ policy, T gamma, T* residual, const T* gate, T gate_thr) {
+  __shared__ T scratch[8];
+  if (gate != nullptr && *gate < gate_thr) return;   // converged earlier: keep V where it is
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = g.row_begin + blockIdx.y * 8 + threadIdx.y;
+  T delta = Num<T>::neg_inf();
+  if (x < g.X && y < g.row_end) {
+    CellIn<T> c;
+    gather_cell(g, vin, x, y, c);
+    const size_t cell = static_cast<size_t>(y - g.row_begin + 1) * g.pitch + x;
+    const T vnew = cell_update<T, KIND>(c, gamma, policy, cell);
+    vout[cell] = vnew;
+    delta = Num<T>::add(c.vs, -vnew);   // V - V_new, signed (dynamic_programming.py:17)
+  }
+  block_max_to_global(delta, scratch, residual);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+greedy_generic_kernel(GridView g, const T* __restrict__ v, uint8_t* __restrict__ tie, T gamma) {
+  const int x = blockIdx.x * 32 + threadIdx.x;
+  const int y = g.row_begin + blockIdx.y * 8 + threadIdx.y;
+  if (x < g.X && y < g.row_end) {
+    CellIn<T> c;
+    gather_cell(g, v, x, y, c);
+    T gn[4];
+    discounted_next(c, gamma, gn);
+    tie[static_cast<size_t>(y - g.row_begin + 1) * g.pitch + x] = static_cast<uint8_t>(tie_mask_of(c, gn));
+  }
+}
+
+template <typename T>
+int sweep_generic(const gu_grid* g, const T* vin, T* vout, int kind, const void* policy, T gamma,
+                  T* residual, const T* gate, T gate_thr, cudaStream_t st) {
+  const GridView v = view_of(g);
+  const int rows = g->row_end - g->row_begin;
+  dim3 block(32, 8), grid((g->X + 31) / 32, (rows + 7) / 8);
+  if (grid.y > 65535u) return GU_ERR_SHAPE;
+  switch (kind) {
+    case GU_POLICY_PROBS:
+      sweep_generic_kernel<T, GU_POLICY_PROBS><<<grid, block, 0, st>>>(v, vin, vout, policy, gamma, residual, gate, gate_thr);
+      break;
+    case GU_POLICY_MASK:
+      sweep_generic_kernel<T, GU_POLICY_MASK><<<grid, block, 0, st>>>(v, vin, vout, policy, gamma, residual, gate, gate_thr);
+      break;
+    case GU_POLICY_UNIFORM:
+      sweep_generic_kernel<T, GU_POLICY_UNIFORM><<<grid, block, 0, st>>>(v, vin, vout, policy, gamma, residual, gate, gate_thr);
+      break;
+    case GU_POLICY_GREEDY:
+      sweep_generic_kernel<T, GU_POLICY_GREEDY><<<grid, block, 0, st>>>(v, vin, vout, policy, gamma, residual, gate, gate_thr);
+      break;
+    default:
+      return GU_ERR_MODE;
+  }
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+template <typename T>
+int greedy_generic(const gu_grid* g, const T* v, uint8_t* tie, T gamma, cudaStream_t st) {
+  const GridView gv = view_of(g);
+  const int rows = g->row_end - g->row_begin;
+  dim3 block(32, 8), grid((g->X + 31) / 32, (rows + 7) / 8);
+  if (grid.y > 65535u) return GU_ERR_SHAPE;
+  greedy_generic_kernel<T><<<grid, block, 0, st>>>(gv, v, tie, gamma);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+// Tiled fast paths (gu_plan_tiled.cu); return GU_ERR_UNSUPPORTED when the shape does not qualify.
+int sweep_tiled_f32(const gu_grid*, const float*, float*, int, const void*, float, float*, const float*,
+                    float, cudaStream_t);
+int sweep_tiled_f64(const gu_grid*, const double*, double*, int, const void*, double, double*, const double*,
+                    double, cudaStream_t);
+int greedy_tiled_f32(const gu_grid*, const float*, uint8_t*, float, cudaStream_t);
+int greedy_tiled_f64(const gu_grid*, const double*, uint8_t*, double, cudaStream_t);
+
+// ---- whole VI loop in one thread block (grids that fit in shared memory) ---------------
+constexpr int kSmallThreads = 1024;
+constexpr int64_t kSmallMaxCells = 13000;   // 2 x f64 + 1 info byte per cell within 227 KB
+
+// info byte: bits 0-3 = blocked per action, bit 4 = goal, bit 5 = lava
+__device__ __forceinline__ void small_cell(const double* va, const uint8_t* info, int s, int X,
+                                           CellIn<double>& c) {
+  const uint32_t i = info[s];
+  c.vs = va[s];
+  c.blk = i & 15u;
+  c.term = (i & 0x30u) != 0;
+  c.rs = reward_of(i & 0x10u, i & 0x20u);
+  const int off[4] = {-X, 1, X, -1};
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    if (!((c.blk >> a) & 1u)) {
+      const int n = s + off[a];
+      const uint32_t j = info[n];
+      c.vn[a] = va[n];
+      c.rn[a] = reward_of(j & 0x10u, j & 0x20u);
+    } else {
+      c.vn[a] = c.vs;
+      c.rn[a] = c.rs;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+vi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ vout,
+                uint8_t* __restrict__ tie, int kind0, const void* __restrict__ policy, double gamma,
+                double threshold, int max_steps, int32_t* sweeps_out, double* last_delta) {
+  extern __shared__ double smem_d[];
+  const int N = g.X * g.Y;
+  double* va = smem_d;
+  double* vb = smem_d + N;
+  uint8_t* info = reinterpret_cast<uint8_t*>(vb + N);
+  __shared__ double red[32];
+  __shared__ double delta_sh;
+  const int tid = threadIdx.x;
+
+  for (int s = tid; s < N; s += kSmallThreads) {
+    const int y = s / g.X, x = s - y * g.X;
+    CellIn<double> c;
+    gather_cell(g, v0, x, y, c);
+    const size_t w = static_cast<size_t>(y + 1) * g.pitch_words + (x >> 5);
+    const uint32_t goal = (g.goal[w] >> (x & 31)) & 1u, lava = (g.lava[w] >> (x & 31)) & 1u;
+    info[s] = static_cast<uint8_t>(c.blk | (goal << 4) | (lava << 5));
+    va[s] = c.vs;
+  }
+  __syncthreads();
+
+  int sweeps = 0;
+  double delta = 0.0;
+  for (int it = 0; it < max_steps; ++it) {
+    double dmax = -CUDART_INF;
+    for (int s = tid; s < N; s += kSmallThreads) {
+      CellIn<double> c;
+      small_cell(va, info, s, g.X, c);
+      const int y = s / g.X, x = s - y * g.X;
+      const size_t cell = static_cast<size_t>(y + 1) * g.pitch + x;
+      double vnew;
+      if (it == 0 && kind0 == GU_POLICY_PROBS) vnew = cell_update<double, GU_POLICY_PROBS>(c, gamma, policy, cell);
+      else if (it == 0 && kind0 == GU_POLICY_MASK) vnew = cell_update<double, GU_POLICY_MASK>(c, gamma, policy, cell);
+      else if (it == 0 && kind0 == GU_POLICY_UNIFORM) vnew = cell_update<double, GU_POLICY_UNIFORM>(c, gamma, policy, cell);
+      else vnew = cell_update<double, GU_POLICY_GREEDY>(c, gamma, policy, cell);
+      vb[s] = vnew;
+      const double d = __dadd_rn(c.vs, -vnew);
+      dmax = d > dmax ? d : dmax;
+    }
+    dmax = warp_max(dmax);
+    if ((tid & 31) == 0) red[tid >> 5] = dmax;
+    __syncthreads();
+    if (tid < 32) {
+      double w = warp_max(red[tid]);
+      if (tid == 0) delta_sh = w;
+    }
+    __syncthreads();
+    delta = delta_sh;
+    double* t = va; va = vb; vb = t;
+    ++sweeps;
+    if (delta < threshold) break;   // dynamic_programming.py:22-23 (uniform across the block)
+  }
+
+  for (int s = tid; s < N; s += kSmallThreads) {
+    CellIn<double> c;
+    small_cell(va, info, s, g.X, c);
+    double gn[4];
+    discounted_next(c, gamma, gn);
+    const int y = s / g.X, x = s - y * g.X;
+    const size_t cell = static_cast<size_t>(y + 1) * g.pitch + x;
+    vout[cell] = c.vs;
+    tie[cell] = static_cast<uint8_t>(tie_mask_of(c, gn));
+  }
+  if (tid == 0) {
+    *sweeps_out = sweeps;
+    *last_delta = delta;
+  }
+}
+
+}  // namespace gu
+
+using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_sweep_f64(const gu_grid* g, const double* v_in, double* v_out, int policy_kind,
+                            const void* policy, double gamma, double* residual, const double* gate,
+                            double gate_threshold, void* stream) {
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (!v_in || !v_out) return GU_ERR_NULL;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  rc = sweep_tiled_f64(g, v_in, v_out, policy_kind, policy, gamma, residual, gate, gate_threshold,
+                       static_cast<cudaStream_t>(stream));
+  if (rc != GU_ERR_UNSUPPORTED) return rc;
+  return sweep_generic<double>(g, v_in, v_out, policy_kind, policy, gamma, residual, gate, gate_threshold,
+                               static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_sweep_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_kind,
+                            const void* policy, float gamma, float* residual, const float* gate,
+                            float gate_threshold, void* stream) {
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (!v_in || !v_out) return GU_ERR_NULL;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  rc = sweep_tiled_f32(g, v_in, v_out, policy_kind, policy, gamma, residual, gate, gate_threshold,
+                       static_cast<cudaStream_t>(stream));
+  if (rc != GU_ERR_UNSUPPORTED) return rc;
+  return sweep_generic<float>(g, v_in, v_out, policy_kind, policy, gamma, residual, gate, gate_threshold,
+                              static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_greedy_f64(const gu_grid* g, const double* v, uint8_t* tie_mask, double gamma, void* stream) {
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (!v || !tie_mask) return GU_ERR_NULL;
+  rc = greedy_tiled_f64(g, v, tie_mask, gamma, static_cast<cudaStream_t>(stream));
+  if (rc != GU_ERR_UNSUPPORTED) return rc;
+  return greedy_generic<double>(g, v, tie_mask, gamma, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_greedy_f32(const gu_grid* g, const float* v, uint8_t* tie_mask, float gamma, void* stream) {
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (!v || !tie_mask) return GU_ERR_NULL;
+  rc = greedy_tiled_f32(g, v, tie_mask, gamma, static_cast<cudaStream_t>(stream));
+  if (rc != GU_ERR_UNSUPPORTED) return rc;
+  return greedy_generic<float>(g, v, tie_mask, gamma, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t gu_vi_small_max_cells(void) { return kSmallMaxCells; }
+
+extern "C" __attribute__((visibility("default"))) int gu_vi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* tie_mask,
+                               int policy_kind, const void* policy, double gamma, double threshold,
+                               int32_t max_steps, int32_t* sweeps_out, double* last_delta, void* stream) {
+  int rc = check_grid(g);
+  if (rc) return rc;
+  if (!v0 || !v_out || !tie_mask || !sweeps_out || !last_delta) return GU_ERR_NULL;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  if (policy_kind < 0 || policy_kind > GU_POLICY_GREEDY) return GU_ERR_MODE;
+  const int64_t N = static_cast<int64_t>(g->X) * g->Y;
+  if (g->row_begin != 0 || g->row_end != g->Y || N > kSmallMaxCells || max_steps < 0) return GU_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(N) * 17 + 16;
+  cudaError_t e = cudaFuncSetAttribute(vi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  vi_small_kernel<<<1, kSmallThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      view_of(g), v0, v_out, tie_mask, policy_kind, policy, gamma, threshold, max_steps, sweeps_out,
+      last_delta);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

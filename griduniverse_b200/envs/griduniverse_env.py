@@ -1,0 +1,174 @@
+"""GridUniverseEnv -- the reference's single-environment API on the B200 kernels.
+
+Same constructor, attributes, return conventions and error behaviour as
+core/envs/griduniverse_env.py:14-321 of the reference; the transition itself
+(`step` / `look_step_ahead`) runs in the batched CUDA kernel with a batch of one, so a
+single call costs one launch + one device->host read.  There is no CPU transition code in
+this class: without a CUDA device `step` raises.  Use ``GridUniverseVecEnv`` for throughput.
+
+Not carried over: the pyglet viewer (`render(mode='graphic')`, `render_policy_arrows`) --
+GUI, out of scope.
+"""
+import random
+import sys
+
+import numpy as np
+from six import StringIO
+
+from ..level import Level, parse_level_text, read_level_file
+from ..spaces import Discrete
+
+
+class GridUniverseEnv(object):
+    metadata = {'render.modes': ['human', 'ansi']}
+
+    def __init__(self, grid_shape=(4, 4), *, initial_state=0, goal_states=None, lava_states=None, walls=None,
+                 custom_world_fp=None, random_maze=False, device="cuda"):
+        # parameter checks: griduniverse_env.py:35-43
+        if goal_states is not None and not isinstance(goal_states, list):
+            raise TypeError("goal_states parameter must be a list of integer indices")
+        if lava_states is not None and not isinstance(lava_states, list):
+            raise TypeError("lava_states parameter must be a list of integer indices")
+        if walls is not None and not isinstance(walls, list):
+            raise TypeError("walls parameter must be a list of integer indices")
+        if not (isinstance(grid_shape, list) or isinstance(grid_shape, tuple)) or len(grid_shape) != 2 \
+                or not isinstance(grid_shape[0], int) or not isinstance(grid_shape[1], int):
+            raise TypeError("grid_shape parameter must be tuple/list of two integers")
+        self._device = device
+        self._vec = None
+        self.action_space = Discrete(4)
+        self.action_descriptors = ['UP', 'RIGHT', 'DOWN', 'LEFT']
+        self.action_descriptor_to_int = {desc: idx for idx, desc in enumerate(self.action_descriptors)}
+        if isinstance(initial_state, int):
+            initial_state = [initial_state]
+        self.num_previous_states_to_store = 500
+        self.last_n_states = []
+        self.done = False
+        self.info = {}
+        self.viewer = None
+        self._install_level(Level(grid_shape[0], grid_shape[1], walls=walls, goals=goal_states,
+                                  lavas=lava_states, starts=initial_state))
+        # observation_space keeps the constructor's shape even if a level file replaces the
+        # world afterwards (reference quirk, griduniverse_env.py:59; algorithms use world.size)
+        self.observation_space = Discrete(self.world.size)
+        self.previous_state = self.current_state = self.initial_state = random.choice(self.starting_states)
+        if custom_world_fp:
+            self._create_custom_world_from_file(custom_world_fp)
+        if random_maze:
+            raise NotImplementedError(
+                "random_maze=True relies on the reference's serial maze generator "
+                "(core/envs/maze_generation.py), which is out of scope for the B200 hot path; "
+                "generate the level text elsewhere and pass custom_world_fp / from_text_lines()")
+
+    # ------------------------------------------------------------------ level plumbing
+    def _install_level(self, level):
+        self.level = level
+        self.x_max, self.y_max = level.X, level.Y
+        # `world` is only used for its .size and (x, y) lookups (griduniverse_env.py:109-118)
+        self.world = np.fromiter(((x, y) for y in range(self.y_max) for x in range(self.x_max)),
+                                 dtype='int64, int64')
+        self.starting_states = level.starting_states
+        self.goal_states, self.lava_states, self.wall_indices = level.index_lists()
+        self.wall_grid = level.wall.astype(np.float64)
+        self.reward_matrix = level.rewards()
+        self._vec = None   # device state is rebuilt lazily for the new level
+
+    @classmethod
+    def from_text_lines(cls, lines, device="cuda"):
+        env = cls(device=device)
+        env._create_custom_world_from_text(["".join(l.split()) for l in lines if l.strip()])
+        return env
+
+    def _create_custom_world_from_file(self, fp):
+        self._create_custom_world_from_text(read_level_file(fp))
+
+    def _create_custom_world_from_text(self, text_world_lines):
+        level = parse_level_text(text_world_lines)   # raises ValueError like :278-300
+        self._install_level(level)
+        self.reset()
+
+    def _device_env(self):
+        if self._vec is None:
+            from .vec_env import GridUniverseVecEnv
+            from ..device import EnvLevels
+            vec = GridUniverseVecEnv.__new__(GridUniverseVecEnv)
+            GridUniverseVecEnv.__init__(vec, 1, levels=EnvLevels.shared(self.level, self._device),
+                                        auto_reset=False, device=self._device, use_tables=False)
+            vec.level = self.level
+            self._vec = vec
+        return self._vec
+
+    # ------------------------------------------------------------------ reference API
+    def look_step_ahead(self, state, action, care_about_terminal=True):
+        """griduniverse_env.py:136-155 -> (next_state, reward, is_terminal)."""
+        if not -4 <= action <= 3:
+            raise IndexError("list index out of range")
+        if not 0 <= state < self.world.size:
+            raise IndexError("index {} is out of bounds for axis 0 with size {}".format(state, self.world.size))
+        nxt, rew, term = self._device_env().look_step_ahead(np.array([state], np.int32),
+                                                            np.array([action], np.int32), care_about_terminal)
+        return int(nxt[0]), np.int64(rew[0]), bool(term[0])
+
+    def look_step_ahead_batch(self, states, actions, care_about_terminal=True):
+        """Vector form of look_step_ahead for many (state, action) pairs in one launch."""
+        return self._device_env().look_step_ahead(states, actions, care_about_terminal)
+
+    def _is_wall(self, state):
+        return bool(self.level.wall[state])
+
+    def is_terminal(self, state):
+        return bool(self.level.lava[state] or self.level.goal[state]) if 0 <= state < self.world.size else False
+
+    def is_lava(self, state):
+        return bool(self.level.lava[state]) if 0 <= state < self.world.size else False
+
+    def is_terminal_goal(self, state):
+        return bool(self.level.goal[state]) if 0 <= state < self.world.size else False
+
+    def step(self, action):
+        """griduniverse_env.py:176-185 -> (observation, reward, done, info)."""
+        self.previous_state = self.current_state
+        self.current_state, reward, self.done = self.look_step_ahead(self.current_state, action)
+        self.last_n_states.append(self.world[self.current_state])
+        if len(self.last_n_states) > self.num_previous_states_to_store:
+            self.last_n_states.pop(0)
+        return self.current_state, reward, self.done, self.info
+
+    def reset(self):
+        """griduniverse_env.py:187-193 (same `random.choice` stream as the reference)."""
+        self.done = False
+        self.previous_state = self.current_state = self.initial_state = random.choice(self.starting_states)
+        self.last_n_states = []
+        return self.current_state
+
+    def render(self, mode='human', close=False):
+        """ASCII render (griduniverse_env.py:195-221); glyph precedence x < G < L < #."""
+        if close:
+            return
+        if mode == 'human' or mode == 'ansi':
+            new_world = np.full(self.world.size, 'o', dtype='<U1')
+            new_world[self.current_state] = 'x'
+            for t_state in self.goal_states:
+                new_world[t_state] = 'G'
+            for t_state in self.lava_states:
+                new_world[t_state] = 'L'
+            for w_state in self.wall_indices:
+                new_world[w_state] = '#'
+            outfile = StringIO() if mode == 'ansi' else sys.stdout
+            for row in np.reshape(new_world, (self.y_max, self.x_max)):
+                for state in row:
+                    outfile.write(state + ' ')
+                outfile.write('\n')
+            outfile.write('\n')
+            return outfile
+        raise NotImplementedError("render mode %r: the pyglet viewer is out of scope" % (mode,))
+
+    def seed(self, seed=None):
+        self.np_random = np.random.RandomState(seed)
+        return [seed]
+
+    def close(self):
+        pass
+
+    # old-gym underscore aliases the reference defines (griduniverse_env.py:176,187,195,239,242)
+    _step, _reset, _render, _seed, _close = step, reset, render, seed, close

@@ -1,0 +1,206 @@
+"""Batched GridUniverse front end: N independent env instances stepped by one kernel.
+
+This is the vector-env face of the reference's ``GridUniverseEnv._step`` /
+``look_step_ahead`` (core/envs/griduniverse_env.py:136-155,176-193).  Positions,
+rewards and done flags live on the GPU; ``step`` / ``rollout`` accept either device
+tensors (zero-copy) or host arrays (staged through pinned memory, results returned as
+NumPy arrays -- the end-to-end path).
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from .. import _cabi
+from ..device import EnvLevels, _require_cuda
+from ..level import Level, parse_level_text, read_level_file
+from ..spaces import Discrete
+
+
+class GridUniverseVecEnv(object):
+    """N GridUniverse instances with the same grid shape.
+
+    Levels: either the reference's constructor arguments (one shared level for all envs),
+    ``custom_world_fp`` (shared level from a text file), or ``levels`` -- a list of N
+    ``Level`` objects / an ``EnvLevels`` with per-env bit planes.
+
+    ``auto_reset=True`` restates the callers' ``if done: env.reset()``
+    (examples/griduniverse_env_examples.py:15,22-24) on the device: the observation returned
+    for a done step is still the landing cell, the env then continues from its start state.
+    ``auto_reset=False`` keeps the reference's absorbing terminals.
+    """
+
+    def __init__(self, num_envs, grid_shape=(4, 4), *, initial_state=0, goal_states=None, lava_states=None,
+                 walls=None, custom_world_fp=None, levels=None, auto_reset=True, device="cuda",
+                 use_tables=True):
+        self.num_envs = int(num_envs)
+        self.device = _require_cuda(device)
+        self.auto_reset = bool(auto_reset)
+        self.level = None
+        if isinstance(levels, EnvLevels):
+            self.levels = levels
+        elif levels is not None:
+            assert len(levels) == self.num_envs
+            self.levels = EnvLevels.from_levels(levels, self.device)
+        else:
+            if custom_world_fp:
+                self.level = parse_level_text(read_level_file(custom_world_fp))
+            else:
+                starts = [initial_state] if isinstance(initial_state, int) else list(initial_state)
+                self.level = Level(grid_shape[0], grid_shape[1], walls=walls, goals=goal_states,
+                                   lavas=lava_states, starts=starts)
+            self.levels = EnvLevels.shared(self.level, self.device)
+        if self.levels.per_env:
+            assert self.levels.n_levels == self.num_envs
+        self.x_max, self.y_max = self.levels.X, self.levels.Y
+        self.action_space = Discrete(4)
+        self.observation_space = Discrete(self.x_max * self.y_max)
+        self.action_descriptors = ['UP', 'RIGHT', 'DOWN', 'LEFT']
+        self.action_descriptor_to_int = {d: i for i, d in enumerate(self.action_descriptors)}
+        self.pos = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        self.stats = torch.zeros(2, dtype=torch.int64, device=self.device)   # [reward sum, done count]
+        self._lib = _cabi.lib()
+        self._pinned = {}
+        if use_tables:
+            self.levels.build_tables(self.num_envs)
+        self.reset()
+
+    # ------------------------------------------------------------------ helpers
+    def _flags(self, care_about_terminal=True):
+        f = _cabi.GU_FLAG_AUTO_RESET if self.auto_reset else 0
+        if not care_about_terminal:
+            f |= _cabi.GU_FLAG_NO_CARE_TERMINAL
+        return f
+
+    def _pin(self, name, shape, dtype):
+        buf = self._pinned.get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.dtype != dtype:
+            buf = torch.empty(shape, dtype=dtype, pin_memory=True)
+            self._pinned[name] = buf
+        return buf
+
+    def _to_device_i32(self, arr, name, is_action=False):
+        """Host int array -> device int32 tensor through a pinned staging buffer."""
+        a = np.asarray(arr)
+        if is_action and a.size and (a.max() > 3 or a.min() < -4):
+            raise IndexError("list index out of range")   # what the reference's action list raises
+        stage = self._pin(name, a.shape, torch.int32)
+        stage.numpy()[...] = a
+        return stage.to(self.device, non_blocking=True)
+
+    # ------------------------------------------------------------------ API
+    def reset(self, start_states=None):
+        """Put every env on its start state (griduniverse_env.py:187-193).  With several start
+        states in a shared level the choice is uniform per env (host RNG, numpy)."""
+        if start_states is not None:
+            self.pos.copy_(torch.as_tensor(np.asarray(start_states, dtype=np.int32)).to(self.device))
+        elif self.levels.per_env:
+            self.pos.copy_(self.levels.start)
+        else:
+            starts = self.level.starting_states if self.level is not None else [int(self.levels.start[0])]
+            if len(starts) == 1:
+                self.pos.fill_(int(starts[0]))
+            else:
+                self.pos.copy_(torch.as_tensor(np.random.choice(starts, self.num_envs).astype(np.int32))
+                               .to(self.device))
+        self.stats.zero_()
+        return self.pos.clone()
+
+    def step(self, actions, start_choice=None):
+        """One step for all envs.  Device tensor in -> device tensors out; host array in ->
+        NumPy arrays out.  Returns (obs, reward, done, info)."""
+        host = not torch.is_tensor(actions)
+        a = self._to_device_i32(actions, "actions", True) if host else actions
+        assert a.dtype == torch.int32 and a.numel() == self.num_envs
+        sc = None
+        if start_choice is not None:
+            sc = self._to_device_i32(start_choice, "start_choice") if not torch.is_tensor(start_choice) \
+                else start_choice
+        n = self.num_envs
+        obs = torch.empty(n, dtype=torch.int32, device=self.device)
+        reward = torch.empty(n, dtype=torch.int32, device=self.device)
+        done = torch.empty(n, dtype=torch.uint8, device=self.device)
+        rc = self._lib.gu_step(self.levels.ref(), n, _cabi.ptr(a), _cabi.ptr(self.pos), _cabi.ptr(obs),
+                               _cabi.ptr(reward), _cabi.ptr(done), _cabi.ptr(sc), _cabi.ptr(self.stats),
+                               self._flags(), _cabi.stream_ptr())
+        _cabi.check("gu_step", rc)
+        if not host:
+            return obs, reward, done.bool(), {}
+        h_obs = self._pin("obs", (n,), torch.int32)
+        h_rew = self._pin("reward", (n,), torch.int32)
+        h_done = self._pin("done", (n,), torch.uint8)
+        h_obs.copy_(obs, non_blocking=True)
+        h_rew.copy_(reward, non_blocking=True)
+        h_done.copy_(done, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return h_obs.numpy().copy(), h_rew.numpy().copy(), h_done.numpy().astype(bool), {}
+
+    def rollout(self, actions, trajectories=False, start_choice=None, per_env=True):
+        """T steps in one launch.  ``actions`` int32 [T, N] (device tensor or host array).
+
+        Returns a dict: ``pos`` (final), ``env_return`` / ``env_done`` per env, ``stats``
+        (int64 [reward sum, done count] accumulated since reset) and, with
+        ``trajectories=True``, ``obs`` / ``reward`` / ``done`` [T, N].  Host input gives NumPy
+        outputs (copied back through pinned memory)."""
+        host = not torch.is_tensor(actions)
+        a = self._to_device_i32(actions, "roll_actions", True) if host else actions
+        assert a.dtype == torch.int32 and a.dim() == 2 and a.shape[1] == self.num_envs and a.is_contiguous()
+        T, n = int(a.shape[0]), self.num_envs
+        sc = None
+        if start_choice is not None:
+            sc = self._to_device_i32(start_choice, "roll_start_choice") if not torch.is_tensor(start_choice) \
+                else start_choice
+        obs = reward = done = env_ret = env_done = None
+        if trajectories:
+            obs = torch.empty((T, n), dtype=torch.int32, device=self.device)
+            reward = torch.empty((T, n), dtype=torch.int32, device=self.device)
+            done = torch.empty((T, n), dtype=torch.uint8, device=self.device)
+        if per_env:
+            env_ret = torch.empty(n, dtype=torch.int32, device=self.device)
+            env_done = torch.empty(n, dtype=torch.int32, device=self.device)
+        rc = self._lib.gu_rollout(self.levels.ref(), n, T, _cabi.ptr(a), _cabi.ptr(self.pos), _cabi.ptr(obs),
+                                  _cabi.ptr(reward), _cabi.ptr(done), _cabi.ptr(sc), _cabi.ptr(env_ret),
+                                  _cabi.ptr(env_done), _cabi.ptr(self.stats), _cabi.ptr(self.levels.tables),
+                                  self._flags(), _cabi.stream_ptr())
+        _cabi.check("gu_rollout", rc)
+        out = {"pos": self.pos, "env_return": env_ret, "env_done": env_done, "stats": self.stats,
+               "obs": obs, "reward": reward, "done": done}
+        if not host:
+            return out
+        res = {}
+        for k, v in out.items():
+            if v is None:
+                res[k] = None
+                continue
+            h = self._pin("roll_" + k, tuple(v.shape), v.dtype)
+            h.copy_(v, non_blocking=True)
+            res[k] = h
+        torch.cuda.current_stream().synchronize()
+        return {k: (None if v is None else v.numpy().copy()) for k, v in res.items()}
+
+    def look_step_ahead(self, states, actions, care_about_terminal=True):
+        """Batched look_step_ahead (griduniverse_env.py:136-155) -> (next, reward, terminal).
+        Shared level: any number of pairs; per-env levels: pair i is evaluated on level i."""
+        host = not torch.is_tensor(states)
+        s = self._to_device_i32(states, "lsa_states") if host else states
+        a = self._to_device_i32(actions, "lsa_actions", True) if not torch.is_tensor(actions) else actions
+        m = int(s.numel())
+        assert a.numel() == m and (not self.levels.per_env or m == self.num_envs)
+        nxt = torch.empty(m, dtype=torch.int32, device=self.device)
+        rew = torch.empty(m, dtype=torch.int32, device=self.device)
+        term = torch.empty(m, dtype=torch.uint8, device=self.device)
+        flags = 0 if care_about_terminal else _cabi.GU_FLAG_NO_CARE_TERMINAL
+        rc = self._lib.gu_look_step_ahead(self.levels.ref(), m, _cabi.ptr(s), _cabi.ptr(a), _cabi.ptr(nxt),
+                                          _cabi.ptr(rew), _cabi.ptr(term), flags, _cabi.stream_ptr())
+        _cabi.check("gu_look_step_ahead", rc)
+        if not host:
+            return nxt, rew, term.bool()
+        return nxt.cpu().numpy(), rew.cpu().numpy(), term.cpu().numpy().astype(bool)
+
+    @property
+    def episode_return_sum(self):
+        return int(self.stats[0])
+
+    @property
+    def done_count(self):
+        return int(self.stats[1])

@@ -1,0 +1,219 @@
+/* gu_b200.h -- C ABI of the B200-native GridUniverse hot path (libgu_b200.so).
+ *
+ * The reference (TheMTank/GridUniverse) is pure Python and has no FFI; the
+ * boundary a replacement sits behind is its Python API.  Each entry point below
+ * replaces the reference function cited next to it (paths relative to the
+ * reference root) for a whole batch / whole grid at once.  INTEGRATION.md shows
+ * the ctypes stub a maintainer would add on the reference side.
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes.  Every pointer inside the descriptor
+ *    structs and every array argument is a DEVICE pointer owned by the caller;
+ *    the library never allocates, frees or keeps a pointer after the call.
+ *    (`*_host` helpers are the exception and say so.)
+ *  - Every call only enqueues work on `stream` (a cudaStream_t passed as void*).
+ *  - Return value: 0 = ok, <0 = argument error (GU_ERR_*), >0 = cudaError_t.
+ *  - Grid geometry (core/envs/griduniverse_env.py:44-56): X = x_max columns,
+ *    Y = y_max rows, state s = y*X + x, actions 0=UP 1=RIGHT 2=DOWN 3=LEFT.
+ *  - Rewards are derived from the masks: lava -10, else goal +10, else -1
+ *    (griduniverse_env.py:80-90; lava is written last and wins).
+ */
+#ifndef GU_B200_H
+#define GU_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GU_OK 0
+#define GU_ERR_NULL (-1)      /* a required pointer is NULL */
+#define GU_ERR_SHAPE (-2)     /* X/Y/N/T/pitch out of the supported range */
+#define GU_ERR_ALIGN (-3)     /* pointer or pitch violates the documented alignment */
+#define GU_ERR_MODE (-4)      /* unknown policy kind / flag / table format */
+#define GU_ERR_UNSUPPORTED (-5)
+
+/* ---- environment batches ------------------------------------------------ */
+
+/* Levels for a batch of N envs that all have the same X x Y shape.
+ * Bit planes are dense: bit (s & 31) of word (s >> 5) is cell s; `words` =
+ * ceil(X*Y/32).  per_env = 0: one shared level, planes are uint32[words],
+ * `start` is int32[1].  per_env = 1: one level per env, planes are WORD-MAJOR
+ * uint32[words][N] (word w of env n at w*N + n, so a warp reading one word for
+ * 32 consecutive envs is one coalesced request), `start` is int32[N].
+ * Replaces wall_grid / goal_states / lava_states / reward_matrix /
+ * starting_states (griduniverse_env.py:61-90,120-134). */
+typedef struct {
+  int32_t X, Y;
+  int32_t per_env;
+  int32_t words;
+  const uint32_t* wall;
+  const uint32_t* goal;
+  const uint32_t* lava;
+  const int32_t* start;
+} gu_levels;
+
+#define GU_FLAG_AUTO_RESET 1u      /* after a done step the env continues from its start state */
+#define GU_FLAG_NO_CARE_TERMINAL 2u /* care_about_terminal=False (griduniverse_env.py:150-153) */
+
+/* One step for N envs: GridUniverseEnv._step (griduniverse_env.py:176-185) =
+ * look_step_ahead(current_state, action) (:136-155) for every env.
+ *   actions int32[N]   (only the two low bits are used: -1 is LEFT like the
+ *                       reference's negative list index; the host validates >3)
+ *   pos     int32[N]   in: current states, out: states the envs continue from
+ *   obs     int32[N]   out: the landing cell `step` returns (may be NULL)
+ *   reward  int32[N]   out, done uint8[N] out (either may be NULL)
+ *   start_choice int32[N] or NULL: start state to use if env n resets now
+ *                       (host-supplied stand-in for random.choice, :189)
+ *   stats   int64[2] or NULL: += sum of rewards, += number of done flags
+ */
+int gu_step(const gu_levels* lv, int64_t n_envs, const int32_t* actions, int32_t* pos,
+            int32_t* obs, int32_t* reward, uint8_t* done, const int32_t* start_choice,
+            int64_t* stats, uint32_t flags, void* stream);
+
+/* T steps for N envs in one launch (run_episode's inner loop,
+ * core/algorithms/monte_carlo.py:19-25, with host-supplied action streams).
+ *   actions int32[T][N];  pos int32[N] in/out
+ *   obs int32[T][N], reward int32[T][N], done uint8[T][N]: trajectories, each may be NULL
+ *   start_choice int32[T][N] or NULL
+ *   env_return int32[N] / env_done int32[N] or NULL: per-env reward sum / done count (overwritten)
+ *   stats int64[2] or NULL as in gu_step (warp-shuffle reduced, one atomic per warp)
+ *   tables: NULL, or transition tables built by gu_pack_tables for the same levels
+ */
+int gu_rollout(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const int32_t* actions,
+               int32_t* pos, int32_t* obs, int32_t* reward, uint8_t* done,
+               const int32_t* start_choice, int32_t* env_return, int32_t* env_done,
+               int64_t* stats, const uint32_t* tables, uint32_t flags, void* stream);
+
+/* Policy-driven episodes: run_episode (core/algorithms/monte_carlo.py:7-26) for N
+ * episodes on one SHARED level, the randomness host-supplied as uniform draws.
+ *   cdf      f64[cells][4]  cumulative action probabilities per state, built exactly like
+ *                           np.random.choice does (p.cumsum(); cdf /= cdf[-1])
+ *   uniforms f64[T][N]      draw t of episode n; action = #{a : cdf[s][a] <= u}
+ *                           (searchsorted side='right', monte_carlo.py:20)
+ *   pos      int32[N]       in: start states, out: final states
+ *   obs int32[T][N], reward int32[T][N] trajectories (entries past an episode's end are
+ *   left untouched), length int32[N] = steps taken (<= T), done uint8[N]; any may be NULL.
+ * An episode stops at its first done step (monte_carlo.py:24-25). */
+int gu_rollout_policy(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const double* cdf,
+                      const double* uniforms, int32_t* pos, int32_t* obs, int32_t* reward,
+                      int32_t* length, uint8_t* done, void* stream);
+
+/* One episode's contribution to Monte-Carlo evaluation (monte_carlo.py:53-91).
+ *   start int32[1] device, obs / rewards: the episode's trajectory as written by
+ *   gu_rollout_policy (element t at t*stride), episode_len = steps taken (L)
+ *   weights f64[>=L]: discount**i, keep uint8[>=L]: discount**i > threshold (built on the
+ *   host with the interpreter's float pow, like the reference's expression at :69-70)
+ *   every_visit: 0 = first-visit, 1 = every-visit
+ *   mode: 0 = incremental mean, stationary (V += (G-V)/N for every state with N > 0)
+ *         1 = incremental, constant alpha  (V += alpha*(G-V) for every state)
+ *         2 = batch: only total_visits / total_return are accumulated (finalize later)
+ *   g_scratch f64[L+1]; total_visits / total_return / value f64[cells], updated in place.
+ * Sums run left to right in fp64 (the reference's pinned CPython 3.6 `sum`; CPython >= 3.12
+ * compensates float sums and differs in the last bits). */
+int gu_mc_episode_f64(int32_t cells, int32_t episode_len, const int32_t* start, const int32_t* obs,
+                      const int32_t* rewards, int64_t stride, const double* weights,
+                      const uint8_t* keep, int32_t every_visit, int32_t mode, double alpha,
+                      double* g_scratch, double* total_visits, double* total_return, double* value,
+                      void* stream);
+/* V(s) = S(s) / N(s) where N(s) > 0 (monte_carlo.py:93-97). */
+int gu_mc_finalize_f64(int32_t cells, const double* total_visits, const double* total_return,
+                       double* value, void* stream);
+
+/* Size in bytes of the transition tables for (lv, n_envs), 0 if the shape has no table format. */
+int64_t gu_tables_bytes(const gu_levels* lv, int64_t n_envs);
+/* Build transition tables (device) from the bit planes: next state per (cell, action)
+ * with the landing cell's goal/lava flags, word-major like the planes. */
+int gu_pack_tables(const gu_levels* lv, int64_t n_envs, uint32_t* tables, uint32_t flags, void* stream);
+
+/* look_step_ahead for M arbitrary (state, action) pairs (griduniverse_env.py:136-155).
+ * Shared level: any M.  per_env levels: pair i is evaluated on level i (M == N).
+ *   states int32[M], actions int32[M] -> next int32[M], reward int32[M], terminal uint8[M] */
+int gu_look_step_ahead(const gu_levels* lv, int64_t m, const int32_t* states, const int32_t* actions,
+                       int32_t* next, int32_t* reward, uint8_t* terminal, uint32_t flags, void* stream);
+
+/* ---- whole-grid planning ------------------------------------------------ */
+
+/* One grid, or one row shard of it, for the sweep / greedy kernels.
+ * The shard owns rows [row_begin, row_end) of a Y-row grid.  EVERY per-cell
+ * array (value functions, policies, tie masks) holds (row_end-row_begin+2) rows
+ * of `pitch` elements: array row 0 is the ghost row above the shard, the last
+ * row the ghost row below (filled by the halo exchange; never read at the true
+ * grid edges).  The bit planes hold the same rows with `pitch_words` uint32 per
+ * row, bit (x & 31) of word (x >> 5); bits at x >= X are zero.
+ * pitch >= X; for the tiled kernels pitch*sizeof(T) % 16 == 0. */
+typedef struct {
+  int32_t X, Y;
+  int32_t row_begin, row_end;
+  int32_t pitch;
+  int32_t pitch_words;
+  const uint32_t* wall;
+  const uint32_t* goal;
+  const uint32_t* lava;
+} gu_grid;
+
+#define GU_POLICY_PROBS 0   /* policy = T[cells][4] probabilities (any stochastic policy) */
+#define GU_POLICY_MASK 1    /* policy = uint8[cells] tie masks: prob 1/popcount on set bits */
+#define GU_POLICY_UNIFORM 2 /* policy = NULL: 1/4 everywhere (policy0 of the examples) */
+#define GU_POLICY_GREEDY 3  /* policy = NULL: tie set recomputed from v_in in the same pass (VI) */
+
+/* One synchronous sweep, single_step_policy_evaluation (core/algorithms/utils.py:15-27):
+ *   v_out[s] = (((R[s] + p0*(g*v[n0])) + p1*(g*v[n1])) + p2*(g*v[n2])) + p3*(g*v[n3])
+ * in the reference's left-to-right order without fused multiply-add.  With
+ * GU_POLICY_GREEDY the policy is greedy_policy_from_value_function(v_in)
+ * (utils.py:55-72), i.e. one value-iteration pass (dynamic_programming.py:16-20).
+ *   residual: T* device scalar, combined with max(v_in - v_out) (signed,
+ *   dynamic_programming.py:17) by atomic max; caller initialises it to -inf. May be NULL.
+ *   gate / gate_threshold: if gate != NULL and *gate < gate_threshold when the kernel
+ *   starts, the sweep is a no-op (v_out and residual untouched).  Passing the previous
+ *   sweep's residual and the convergence threshold lets a caller enqueue many sweeps
+ *   without a host round trip: the ones after convergence (dynamic_programming.py:22-23)
+ *   do nothing and the converged V stays where it was written. */
+int gu_sweep_f64(const gu_grid* g, const double* v_in, double* v_out, int policy_kind,
+                 const void* policy, double gamma, double* residual, const double* gate,
+                 double gate_threshold, void* stream);
+int gu_sweep_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_kind,
+                 const void* policy, float gamma, float* residual, const float* gate,
+                 float gate_threshold, void* stream);
+
+/* greedy_policy_from_value_function (utils.py:55-72) as a tie mask per cell:
+ * bit a set <=> rint(q[s,a]*1e8) == rint(max_a q[s,a]*1e8) and s is not terminal,
+ * q[s,a] = R[next] + g*v[next].  np.argmax of the expanded row is ctz(mask). */
+int gu_greedy_f64(const gu_grid* g, const double* v, uint8_t* tie_mask, double gamma, void* stream);
+int gu_greedy_f32(const gu_grid* g, const float* v, uint8_t* tie_mask, float gamma, void* stream);
+
+/* Whole value_iteration loop (dynamic_programming.py:8-28) for a grid small enough to
+ * live in one thread block's shared memory (see gu_vi_small_max_cells): sweeps until
+ * max(V - V') < threshold or max_steps, then writes V, the tie masks of the final V,
+ * and the number of sweeps done.  Arrays use the padded layout of gu_grid; the shard
+ * must be the whole grid.
+ *   policy_kind/policy describe the caller's initial policy (used by the first sweep). */
+int gu_vi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* tie_mask,
+                    int policy_kind, const void* policy, double gamma, double threshold,
+                    int32_t max_steps, int32_t* sweeps_out, double* last_delta, void* stream);
+int64_t gu_vi_small_max_cells(void);
+
+/* ---- synthetic levels (not in the reference; pure functions of seed and index) -------- */
+
+/* Per-env levels for envs [first_env, first_env + n_envs): border open, 20 % interior walls,
+ * one goal, X*Y/32 lava draws, one start on an open non-terminal cell.  X*Y <= 256.
+ * Planes WORD-MAJOR uint32[words][n_envs], start int32[n_envs] (see gu_levels). */
+int gu_synth_env_levels(int32_t X, int32_t Y, int64_t n_envs, int64_t first_env, uint32_t seed,
+                        uint32_t* wall, uint32_t* goal, uint32_t* lava, int32_t* start, void* stream);
+
+/* Maze planes in the gu_grid layout for rows [row_begin-1, row_end+1): (x,y) is a wall iff
+ * x,y both odd, or exactly one is odd and hash(seed,y,x) < 1/4; goal at the (even,even) cell
+ * next to the centre; open cells are lava with probability 0.001. */
+int gu_synth_maze(int32_t X, int32_t Y, int32_t row_begin, int32_t row_end, int32_t pitch_words,
+                  uint32_t seed, uint32_t* wall, uint32_t* goal, uint32_t* lava, void* stream);
+
+/* ---- queries -------------------------------------------------------------- */
+int gu_version(void);                 /* 10000*major + 100*minor + patch */
+const char* gu_arch(void);            /* "sm_100a" */
+const char* gu_error_string(int code);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GU_B200_H */

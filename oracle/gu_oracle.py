@@ -357,8 +357,12 @@ def mc_accumulate_episode(states, rewards, N, every_visit, discount_factor, thre
         elif not every_visit:
             continue
         visits[s] += 1
-        g = sum([(discount_factor ** i) * r for i, r in enumerate(rewards[idx:])
-                 if (discount_factor ** i) > threshold])
+        # monte_carlo.py:69-70.  Plain left-to-right adds = `sum` of the reference's pinned
+        # CPython 3.6 (CPython >= 3.12 compensates float sums; see tests/golden/make_golden.py).
+        g = 0
+        for i, r in enumerate(rewards[idx:]):
+            if (discount_factor ** i) > threshold:
+                g = g + (discount_factor ** i) * r
         returns[s] += g
     return visits, returns
 

@@ -304,25 +304,44 @@ def main():
                 "every_batch": dict(every_visit=True, incremental_mean=False),
                 "first_alpha": dict(every_visit=False, stationary_env=False, alpha=0.01)}
     orig_run = ref.mc.run_episode
-    for vname, kw in variants.items():
-        random.seed(5)
-        np.random.seed(5)
-        eps = []
 
-        def rec(policy, env_, max_steps_per_episode=1000):
-            out = orig_run(policy, env_, max_steps_per_episode)
-            eps.append(out)
-            return out
+    def naive_sum(terms):
+        """CPython < 3.12 `sum` for floats: plain left-to-right adds.  The reference pins
+        python 3.6.3 (requirements.yml:14); CPython >= 3.12 compensates float sums, which
+        changes the last bits of monte_carlo.py:69-70.  Injected as a module global so the
+        reference source stays untouched."""
+        acc = 0
+        for t in terms:
+            acc = acc + t
+        return acc
 
-        ref.mc.run_episode = rec
-        with quiet():
-            V = ref.mc.monte_carlo_evaluation(pol, env, num_episodes=4, **kw)
-        ref.mc.run_episode = orig_run
-        npz["mc/%s/V" % vname] = V
-        for i, (st, rw, d) in enumerate(eps):
-            npz["mc/%s/ep%d/states" % (vname, i)] = np.array(st, np.int64)
-            npz["mc/%s/ep%d/rewards" % (vname, i)] = np.array(rw, np.int64)
-        meta["mc/%s" % vname] = {"kwargs": kw, "episodes": len(eps), "seed": 5}
+    for prefix, summer in (("mc", naive_sum), ("mc312", None)):
+        if summer is not None:
+            ref.mc.sum = summer
+        elif hasattr(ref.mc, "sum"):
+            del ref.mc.sum
+        for vname, kw in variants.items():
+            random.seed(5)
+            np.random.seed(5)
+            eps = []
+
+            def rec(policy, env_, max_steps_per_episode=1000):
+                out = orig_run(policy, env_, max_steps_per_episode)
+                eps.append(out)
+                return out
+
+            ref.mc.run_episode = rec
+            with quiet():
+                V = ref.mc.monte_carlo_evaluation(pol, env, num_episodes=4, **kw)
+            ref.mc.run_episode = orig_run
+            npz["%s/%s/V" % (prefix, vname)] = V
+            if prefix == "mc":
+                for i, (st, rw, d) in enumerate(eps):
+                    npz["mc/%s/ep%d/states" % (vname, i)] = np.array(st, np.int64)
+                    npz["mc/%s/ep%d/rewards" % (vname, i)] = np.array(rw, np.int64)
+                meta["mc/%s" % vname] = {"kwargs": kw, "episodes": len(eps), "seed": 5}
+    if hasattr(ref.mc, "sum"):
+        del ref.mc.sum
 
     cases["dp_meta"] = meta
     with open(os.path.join(HERE, "levels.json"), "w") as f:

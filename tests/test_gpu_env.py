@@ -1,0 +1,185 @@
+"""GPU parity: batched step / look_step_ahead / rollouts (through the C ABI) against the
+reference's known answers, the golden trajectories and the oracle.  Bit-exact."""
+import random
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import gu_oracle as orc
+from griduniverse_b200 import synth
+from griduniverse_b200.device import EnvLevels
+from griduniverse_b200.envs import GridUniverseEnv, GridUniverseVecEnv
+from griduniverse_b200.level import Level
+
+pytestmark = pytest.mark.gpu
+SHIPPED = ["default_env", "test_env", "maze_11x11", "maze_21x21", "maze_101x101"]
+
+
+def make_env(case, golden_levels):
+    if case.get("level"):
+        env = GridUniverseEnv.from_text_lines(golden_levels[case["level"]])
+    else:
+        kw = dict(case["ctor"])
+        if "grid_shape" in kw:
+            kw["grid_shape"] = tuple(kw["grid_shape"])
+        env = GridUniverseEnv(**kw)
+    return env
+
+
+def test_reference_unit_tests_known_answers(golden_cases, golden_levels):
+    """tests/test_griduniverse.py:49-176 through GridUniverseEnv.step (one launch per step)."""
+    for case in golden_cases["unit_tests"]:
+        env = make_env(case, golden_levels)
+        env.current_state = case["start"]
+        for a, exp in zip(case["actions"], case["expect"]):
+            o, r, d, info = env.step(a)
+            assert [o, int(r), d] == exp and info == {}, case["name"]
+    # the assertions the reference tests make themselves
+    env = GridUniverseEnv(walls=[1])
+    assert env.step(1)[0] == 0
+    env = GridUniverseEnv()
+    dones = [env.step(a)[2] for a in [1, 1, 1, 2, 2, 2]]
+    assert dones == [False] * 5 + [True]
+    env = GridUniverseEnv(grid_shape=(25, 30))
+    dones = [env.step(a)[2] for a in [1] * 24 + [2] * 29]
+    assert dones.index(True) == 52
+    env = GridUniverseEnv(lava_states=[1])
+    o, r, d, _ = env.step(env.action_descriptor_to_int['RIGHT'])
+    assert r == -10 and d
+    env = GridUniverseEnv()
+    prev, hits = env.reset(), []
+    for i, a in enumerate([3, 0, 1, 1, 1, 1, 2, 2, 3, 2, 2, 3, 3, 3]):
+        o = env.step(a)[0]
+        if o == prev:
+            hits.append(i)
+        prev = o
+    assert hits == [0, 1, 5, 10, 13]
+    with pytest.raises(IndexError):
+        env.step(4)
+    assert env.look_step_ahead(5, -1)[0] == 4      # -1 is LEFT, like the reference's list index
+
+
+def test_probes(golden_cases):
+    for p in golden_cases["probes"]:
+        if p["name"] == "absorbing_lava":
+            env = GridUniverseEnv(**p["ctor"])
+            for a, exp in zip(p["actions"], p["expect"]):
+                o, r, d, _ = env.step(a)
+                assert [o, int(r), d] == exp
+        if p["name"] == "no_care_from_lava":
+            env = GridUniverseEnv(**p["ctor"])
+            n, r, d = env.look_step_ahead(p["look"][0], p["look"][1], care_about_terminal=p["look"][2])
+            assert [n, int(r), d] == p["expect"]
+
+
+def test_look_step_ahead_full_tables(golden, golden_levels):
+    for name in golden_levels:
+        if name == "maze_101x101":
+            continue
+        env = GridUniverseEnv.from_text_lines(golden_levels[name])
+        N = env.world.size
+        s, a = np.divmod(np.arange(N * 4, dtype=np.int32), 4)
+        for care, key in ((True, "lsa/"), (False, "lsa_nc/")):
+            tab = golden[key + name].reshape(N * 4, 3)
+            n, r, t = env.look_step_ahead_batch(s.astype(np.int32), a.astype(np.int32), care)
+            assert np.array_equal(n, tab[:, 0]) and np.array_equal(r, tab[:, 1])
+            assert np.array_equal(t, tab[:, 2].astype(bool))
+
+
+@pytest.mark.parametrize("name", SHIPPED)
+def test_golden_trajectories_rollout_and_step(golden, golden_levels, name):
+    lv_lines = golden_levels[name]
+    acts = golden["traj/%s/actions" % name].astype(np.int32)
+    sc = golden["traj/%s/start_choice" % name].astype(np.int32)
+    start = int(golden["traj/%s/start" % name])
+    # whole trajectory in one launch (auto-reset with the host-supplied start choices)
+    from griduniverse_b200.level import parse_level_text
+    level = parse_level_text(orc.strip_level_lines(lv_lines))
+    env = GridUniverseVecEnv(1, levels=EnvLevels.shared(level), auto_reset=True)
+    env.reset([start])
+    out = env.rollout(acts[:, None], trajectories=True, start_choice=np.maximum(sc, 0)[:, None])
+    assert np.array_equal(out["obs"][:, 0], golden["traj/%s/obs" % name])
+    assert np.array_equal(out["reward"][:, 0], golden["traj/%s/reward" % name])
+    assert np.array_equal(out["done"][:, 0].astype(bool), golden["traj/%s/done" % name])
+    assert int(out["stats"][0]) == int(golden["traj/%s/reward" % name].sum())
+    assert int(out["stats"][1]) == int(golden["traj/%s/done" % name].sum())
+    # the same trajectory one step per launch through the reference-style env, reset() on done
+    genv = GridUniverseEnv.from_text_lines(lv_lines)
+    genv.current_state = start
+    for t in range(120):
+        o, r, d, _ = genv.step(int(acts[t]))
+        assert (o, int(r), d) == (golden["traj/%s/obs" % name][t], golden["traj/%s/reward" % name][t],
+                                  golden["traj/%s/done" % name][t])
+        if d:
+            genv.reset()
+            genv.current_state = int(sc[t])
+
+
+def test_cfg1_default_env_1000_steps(golden):
+    """BASELINE cfg 1: default 4x4, RandomState(0) actions, reset() on done."""
+    acts = np.random.RandomState(0).randint(0, 4, 1000).astype(np.int32)
+    env = GridUniverseVecEnv(1, auto_reset=True)
+    out = env.rollout(acts[:, None], trajectories=True)
+    assert np.array_equal(out["obs"][:, 0], golden["cfg1/obs"])
+    assert np.array_equal(out["reward"][:, 0], golden["cfg1/reward"])
+    assert np.array_equal(out["done"][:, 0].astype(bool), golden["cfg1/done"])
+
+
+@pytest.mark.parametrize("shape,n,T", [((8, 8), 1024, 96), ((16, 16), 1024, 128), ((8, 8), 1001, 33),
+                                       ((5, 7), 130, 50)])
+@pytest.mark.parametrize("auto_reset", [True, False])
+def test_per_env_levels_vs_oracle(shape, n, T, auto_reset):
+    """cfg 3 / cfg 4 shapes (and ragged sizes): per-env synthetic levels, random actions."""
+    X, Y = shape
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, seed=0)
+    levels = [Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    olevels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    actions = np.random.RandomState(1).randint(0, 4, (T, n)).astype(np.int32)
+    exp_obs, exp_rew, exp_done, exp_pos = orc.rollout(olevels, start, actions, auto_reset=auto_reset)
+    for use_tables in (False, True):
+        env = GridUniverseVecEnv(n, levels=levels, auto_reset=auto_reset, use_tables=use_tables)
+        out = env.rollout(actions, trajectories=True)
+        assert np.array_equal(out["obs"], exp_obs) and np.array_equal(out["reward"], exp_rew)
+        assert np.array_equal(out["done"].astype(bool), exp_done) and np.array_equal(out["pos"], exp_pos)
+        assert np.array_equal(out["env_return"], exp_rew.sum(axis=0))
+        assert np.array_equal(out["env_done"], exp_done.sum(axis=0))
+        assert out["stats"].tolist() == [exp_rew.sum(), exp_done.sum()]
+        # summaries only (no trajectories) give the same final state and counters
+        env2 = GridUniverseVecEnv(n, levels=levels, auto_reset=auto_reset, use_tables=use_tables)
+        out2 = env2.rollout(actions, trajectories=False)
+        assert np.array_equal(out2["pos"], exp_pos) and np.array_equal(out2["env_return"], exp_rew.sum(axis=0))
+    # one step per launch gives the same trajectory
+    env = GridUniverseVecEnv(n, levels=levels, auto_reset=auto_reset)
+    for t in range(min(T, 24)):
+        o, r, d, _ = env.step(actions[t])
+        assert np.array_equal(o, exp_obs[t]) and np.array_equal(r, exp_rew[t]) and np.array_equal(d, exp_done[t])
+
+
+def test_device_level_generator_matches_numpy_twin():
+    for (X, Y, n, first) in ((8, 8, 4096, 0), (16, 16, 1000, 12345), (3, 3, 10, 0)):
+        wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, first_env=first, seed=9)
+        dev = synth.env_levels_device(X, Y, n, first_env=first, seed=9)
+        ref = EnvLevels.from_masks(X, Y, wall, goal, lava, start)
+        for a, b in ((dev.wall, ref.wall), (dev.goal, ref.goal), (dev.lava, ref.lava), (dev.start, ref.start)):
+            assert torch.equal(a, b)
+
+
+def test_shared_level_many_envs_device_tensors(golden_levels):
+    """Shared level, device-resident actions in / device tensors out, multi-start reset."""
+    from griduniverse_b200.level import parse_level_text
+    level = parse_level_text(orc.strip_level_lines(golden_levels["test_env"]))
+    n, T = 4096, 40
+    env = GridUniverseVecEnv(n, levels=EnvLevels.shared(level), auto_reset=True)
+    env.level = level
+    np.random.seed(0)
+    pos0 = env.reset().cpu().numpy()
+    assert set(np.unique(pos0)) == {0, 3}
+    actions = torch.randint(0, 4, (T, n), dtype=torch.int32, device="cuda",
+                            generator=torch.Generator(device="cuda").manual_seed(1))
+    out = env.rollout(actions, trajectories=True)
+    olv = orc.parse_level_text(orc.strip_level_lines(golden_levels["test_env"]))
+    eo, er, ed, ep = orc.rollout(olv, pos0, actions.cpu().numpy(), auto_reset=True)
+    assert np.array_equal(out["obs"].cpu().numpy(), eo) and np.array_equal(out["reward"].cpu().numpy(), er)
+    assert np.array_equal(out["pos"].cpu().numpy(), ep)
+    assert env.done_count == int(ed.sum()) and env.episode_return_sum == int(er.sum())

@@ -1,0 +1,167 @@
+"""Host logic (no GPU): level parser / constructor errors / ASCII render against the
+reference's known answers, the packers, the synthetic generators, and that the C-ABI
+library loads and exports every symbol include/gu_b200.h declares."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import gu_oracle as orc
+from griduniverse_b200 import _cabi, synth
+from griduniverse_b200.envs import GridUniverseEnv
+from griduniverse_b200.level import (Level, pack_dense, pack_env_planes, pack_grid_plane, parse_level_text,
+                                     grid_pitch, grid_pitch_words)
+from griduniverse_b200.planner import masks_to_policy, policy_to_masks
+from griduniverse_b200.algorithms.monte_carlo import _choice_cdf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_header_symbol():
+    with open(os.path.join(ROOT, "include", "gu_b200.h")) as f:
+        header = f.read()
+    declared = set(re.findall(r"\b(gu_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _cabi.lib()
+    for name in declared:
+        assert hasattr(lib, name), "libgu_b200.so does not export %s" % name
+    assert set(_cabi.EXPORTS) == declared
+    assert lib.gu_arch() == b"sm_100a"
+    assert lib.gu_error_string(-1) == b"required pointer is NULL"
+
+
+def test_constructor_errors_match_reference(golden_cases):
+    """tests/test_griduniverse.py:7-47 and griduniverse_env.py:82-90,130-131."""
+    for case in golden_cases["ctor_errors"]:
+        kw = dict(case["kwargs"])
+        if "grid_shape" in kw and isinstance(kw["grid_shape"], list) and len(kw["grid_shape"]) == 3:
+            kw["grid_shape"] = tuple(kw["grid_shape"])
+        exc = {"IndexError": IndexError, "TypeError": TypeError, "ValueError": ValueError}[case["raises"]]
+        with pytest.raises(exc):
+            GridUniverseEnv(**kw)
+    with pytest.raises(TypeError):
+        GridUniverseEnv(grid_shape=set([2, 3]))
+
+
+def test_level_text_parser(golden_levels, tmp_path):
+    for name, lines in golden_levels.items():
+        lv = parse_level_text(orc.strip_level_lines(lines))
+        olv = orc.parse_level_text(orc.strip_level_lines(lines))
+        assert (lv.X, lv.Y) == (olv.X, olv.Y)
+        assert np.array_equal(lv.wall, olv.wall) and np.array_equal(lv.goal, olv.goal)
+        assert np.array_equal(lv.lava, olv.lava) and lv.starting_states == olv.starts
+        assert np.array_equal(lv.rewards(), olv.reward)
+        assert lv.to_text_lines() == orc.strip_level_lines(lines)
+    # file path + whitespace / blank-line stripping (griduniverse_env.py:246-251)
+    fp = tmp_path / "lvl.txt"
+    fp.write_text("x o #\n\n o o G \n")
+    env = GridUniverseEnv(custom_world_fp=str(fp))
+    assert (env.x_max, env.y_max, env.world.size) == (3, 2, 6)
+    assert env.goal_states == [5] and env.wall_indices == [2] and env.starting_states == [0]
+    assert env.observation_space.n == 16      # reference quirk: not refreshed after a level file
+    for bad, msg in ((["xo", "oGo"], "not a rectangle"), (["xoQ", "ooG"], "Invalid Character"),
+                     (["oo", "oG"], "No starting states"), (["xo", "oo"], "No terminal goal")):
+        with pytest.raises(ValueError, match=msg):
+            parse_level_text(bad)
+
+
+def test_ascii_render_and_attributes(golden_cases, golden_levels, tmp_path):
+    for p in golden_cases["probes"]:
+        if p["name"] == "render_ansi_wall1":
+            assert GridUniverseEnv(walls=[1]).render(mode='ansi').getvalue() == p["ansi"]
+        if p["name"] == "render_ansi_test_env":
+            env = GridUniverseEnv.from_text_lines(golden_levels["test_env"])
+            env.current_state = p["state"]
+            assert env.render(mode='ansi').getvalue() == p["ansi"]
+    env = GridUniverseEnv(lava_states=[1])
+    assert env.action_descriptor_to_int['RIGHT'] == 1 and env.action_space.n == 4
+    assert env.is_lava(1) and env.is_terminal(1) and env.is_terminal_goal(15) and not env.is_terminal(0)
+    assert env.reward_matrix[1] == -10 and env.reward_matrix[15] == 10 and env.reward_matrix[0] == -1
+    assert GridUniverseEnv(goal_states=[5], lava_states=[5]).reward_matrix[5] == -10
+
+
+def test_packers():
+    rs = np.random.RandomState(0)
+    m = rs.rand(5, 70) < 0.5
+    w = pack_dense(m)
+    assert w.shape == (5, 3) and w.dtype == np.uint32
+    for s in range(70):
+        assert np.array_equal((w[:, s >> 5] >> (s & 31)) & 1, m[:, s])
+    assert np.array_equal(pack_env_planes(m), w.T)
+    g = rs.rand(9, 45) < 0.5
+    pw = grid_pitch_words(45)
+    assert pw == 4 and grid_pitch(45) == 64 and grid_pitch(16384) == 16384 and grid_pitch_words(16384) == 512
+    plane = pack_grid_plane(g, 3, 7, pw).reshape(6, pw)
+    for ar, y in enumerate(range(2, 8)):
+        for x in range(45):
+            assert ((plane[ar, x >> 5] >> (x & 31)) & 1) == g[y, x]
+    edge = pack_grid_plane(g, 0, 9, pw).reshape(11, pw)
+    assert not edge[0].any() and not edge[-1].any()
+
+
+def test_mask_policy_round_trip():
+    masks = np.arange(16, dtype=np.uint8)
+    pol = masks_to_policy(masks)
+    assert np.array_equal(pol, orc.masks_to_policy(masks))
+    assert np.array_equal(policy_to_masks(pol), masks)
+    assert pol[7].tolist() == [1 / 3, 1 / 3, 1 / 3, 0.0] and pol[0].tolist() == [0, 0, 0, 0]
+    assert policy_to_masks(np.array([[0.1, 0.2, 0.3, 0.4]])) is None
+    assert np.array_equal(policy_to_masks(np.ones((3, 4)) / 4), [15, 15, 15])
+
+
+def test_synthetic_env_levels_are_well_formed():
+    for X, Y in ((8, 8), (16, 16)):
+        wall, goal, lava, start = synth.env_levels_numpy(X, Y, 500, first_env=7, seed=3)
+        cells = X * Y
+        assert goal.sum(axis=1).tolist() == [1] * 500
+        assert not (wall & goal).any() and not (wall & lava).any() and not (goal & lava).any()
+        r = np.arange(500)
+        assert not wall[r, start].any() and not goal[r, start].any() and not lava[r, start].any()
+        border = np.zeros((Y, X), bool)
+        border[0], border[-1], border[:, 0], border[:, -1] = True, True, True, True
+        assert not wall[:, border.reshape(-1)].any()
+        dens = wall[:, ~border.reshape(-1)].mean()
+        assert 0.15 < dens < 0.25
+        assert lava.sum(axis=1).max() <= cells // 32
+        # slices of the env range reproduce the same levels (shard-independent)
+        w2, g2, l2, s2 = synth.env_levels_numpy(X, Y, 100, first_env=107, seed=3)
+        assert np.array_equal(w2, wall[100:200]) and np.array_equal(s2, start[100:200])
+
+
+def test_synthetic_maze_is_shard_independent():
+    wall, goal, lava = synth.maze_numpy(96, 64, seed=0)
+    assert goal.sum() == 1 and goal[32, 48]
+    assert wall[1::2, 1::2].all() and not wall[0::2, 0::2].any()
+    assert 0.2 < wall[0::2, 1::2].mean() < 0.3
+    w2, g2, l2 = synth.maze_numpy(96, 64, seed=0, row_begin=10, row_end=30)
+    assert np.array_equal(w2, wall[10:30]) and np.array_equal(l2, lava[10:30])
+    lvl = synth.maze_level(96, 64, seed=0)
+    assert lvl.N == 96 * 64 and len(lvl.starting_states) == 1
+
+
+def test_choice_cdf_reproduces_numpy_choice():
+    """run_episode draws actions with np.random.choice(4, p=policy[s]) (monte_carlo.py:20); the
+    device picks #{a : cdf[a] <= u} from pre-drawn uniforms -- same actions, same RNG stream."""
+    rs = np.random.RandomState(3)
+    pol = rs.dirichlet(np.ones(4), size=6)
+    pol[2] = [0.25, 0.25, 0.25, 0.25]
+    pol[3] = [0, 0.5, 0.5, 0]
+    cdf = _choice_cdf(pol)
+    states = rs.randint(0, 6, 200)
+    np.random.seed(11)
+    expect = [np.random.choice(4, p=pol[s]) for s in states]
+    np.random.seed(11)
+    u = np.random.random_sample(200)
+    got = [(cdf[s, :3] <= u[i]).sum() for i, s in enumerate(states)]
+    assert expect == got
+    assert np.random.random_sample() == np.random.RandomState(11).random_sample(201)[-1]
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    env = GridUniverseEnv()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        env.step(1)

@@ -178,3 +178,10 @@ def test_fp32_tracks_fp64(golden_levels):
                                       dtype=np.float32)
     assert V32.dtype == np.float32
     assert np.max(np.abs(V32.astype(np.float64) - V64)) < 1e-4
+
+
+def test_monte_carlo_python312_sum_is_close(golden):
+    """The same evaluation run with CPython 3.12's compensated `sum` differs only in the last bits."""
+    for variant in ("first_inc", "every_inc", "every_batch", "first_alpha"):
+        a, b = golden["mc/%s/V" % variant], golden["mc312/%s/V" % variant]
+        assert np.max(np.abs(a - b)) < 1e-12
