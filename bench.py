@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py -- GridUniverse hot-path benchmark (BASELINE.json metric:
+"batched env steps/sec & value-iteration cell-updates/sec, 1/2/4/8 B200").
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched with torchrun)
+    python bench.py --impl reference ...                      (oracle port on the host cores)
+
+Workloads (synthetic levels, random actions):
+  * env (headline line): BASELINE cfg 4 -- 16,777,216 independent 8x8 envs with per-env
+    walls / lava / goal, T = 256 host-supplied actions per env per pass, envs sharded
+    contiguously over the N GPUs with no collective (strong scaling: total fixed).
+    One "step" = one pass = ONE rollout-kernel launch per GPU = 2^32 env steps in total.
+  * vi: BASELINE cfg 5 -- value iteration (gamma 0.9, theta 1e-6, uniform policy0, V0 = 0) on a
+    16384 x 16384 synthetic maze, fp32, row-sharded over the N GPUs with NCCL halo exchange and a
+    residual MAX all-reduce per sweep.  One pass = one full solve.
+  * cfg3: 65,536 16x16 envs, T = 1024 (rank 0 only, extra line inside the JSON).
+
+`value`: inputs resident in HBM.  `e2e`: the same workload through the Python API with HOST
+(pinned) buffers, host<->device copies inside the timed region.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+ENV_TOTAL = 16777216
+ENV_SHAPE = (8, 8)
+ENV_T = 256
+CFG3_N, CFG3_SHAPE, CFG3_T = 65536, (16, 16), 1024
+VI_SIZE = 16384
+VI_GAMMA, VI_THETA = 0.9, 1e-6
+BYTES_PER_STEP_SUMMARY = 4.0          # int32 action per env step, summaries only
+BYTES_PER_CELL_FUSED_F32 = 8.375      # read V + write V' + 3 mask bits
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def profiled_traffic(key):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (or None)."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f).get(key)
+    return None
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, smax, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "power_w_max": max(power), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------
+# reference arm: the oracle port on the host cores
+# ----------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import cpu_baseline as cb
+    procs = os.cpu_count() or 1
+    n_per_proc, T = 32768, 64
+    for _ in range(args.warmup):
+        cb.env_steps_per_sec(ENV_SHAPE[0], ENV_SHAPE[1], n_per_proc, T, procs)
+    t0 = time.perf_counter()
+    vals = [cb.env_steps_per_sec(ENV_SHAPE[0], ENV_SHAPE[1], n_per_proc, T, procs)["value"]
+            for _ in range(args.steps)]
+    wall = time.perf_counter() - t0
+    value = float(np.mean(vals))
+    vi = cb.vi_cell_updates_per_sec(512, 512, 4, procs, dtype=np.float32)
+    sample = ("%d procs x %d 8x8 envs x %d steps per step (oracle NumPy port of "
+              "griduniverse_env.py:136-193), same generator/seed as the GPU arm" % (procs, n_per_proc, T))
+    line = {
+        "impl": "reference", "metric": "env_steps_per_sec", "value": value, "unit": "steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1000.0 * wall / max(args.steps, 1), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+        "config": env_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "steps/s", "cores": procs, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "vi": {"metric": "vi_cell_updates_per_sec", "value": vi["value"], "unit": "cell-updates/s",
+               "cpu_baseline": {"value": vi["value"], "unit": "cell-updates/s", "cores": procs, "kind": "port",
+                                "sample": "%d replicas of a 512x512 synthetic maze, 4 sweep+greedy iterations "
+                                          "each, fp32 oracle" % procs}},
+    }
+    print(json.dumps(line))
+
+
+def env_config(n_gpus):
+    return {"workload": "cfg4: 16,777,216 independent 8x8 envs (per-env walls/lava/goal bit planes), "
+                        "T=256 int32 actions per env per pass, auto-reset, summaries only",
+            "envs_total": ENV_TOTAL, "grid": "8x8", "steps_per_pass": ENV_T, "parallelism": "env-sharded x%d, no collective" % n_gpus,
+            "l2": "inputs larger than L2 (%.1f GB of actions per GPU per pass)" % (ENV_TOTAL / n_gpus * ENV_T * 4 / 1e9)}
+
+
+# ----------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from griduniverse_b200 import synth
+    from griduniverse_b200.envs import GridUniverseVecEnv
+    from griduniverse_b200.planner import Planner
+    from griduniverse_b200.sharded import ShardedValueIteration, shard_envs, shard_rows
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node N for --gpus N"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    peak, peak_src = measured_peak()
+    K, W = args.steps, max(args.warmup, 3)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, iters):
+        """K iterations bracketed by barrier+sync, CUDA events on the launching stream, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / 1000.0
+
+    # ------------------------------------------------------------------ env workload (cfg 4)
+    lo, hi = shard_envs(ENV_TOTAL, world, rank)
+    n_local = hi - lo
+    levels = synth.env_levels_device(ENV_SHAPE[0], ENV_SHAPE[1], n_local, first_env=lo, seed=0, device=dev)
+    env = GridUniverseVecEnv(n_local, levels=levels, auto_reset=True, device=dev)
+    gen = torch.Generator(device=dev).manual_seed(1 + rank)
+    actions = torch.randint(0, 4, (ENV_T, n_local), dtype=torch.int32, device=dev, generator=gen)
+
+    def env_pass():
+        env.rollout(actions, trajectories=False, per_env=True)
+
+    for _ in range(W):
+        env_pass()
+    sampler = ClockSampler(local_rank).start() if rank == 0 else None
+    env.launches = 0
+    t_env = timed(env_pass, K)
+    env_launches = env.launches
+    env_value = float(ENV_TOTAL) * ENV_T * K / t_env
+    env_kernel_s = t_env / K                          # one pass == one rollout launch per GPU
+    env_achieved = BYTES_PER_STEP_SUMMARY * n_local * ENV_T / env_kernel_s / 1e9
+
+    # e2e: host-resident actions streamed through pinned slabs (H2D inside the timed region)
+    slab_t = 16
+    ring = [torch.randint(0, 4, (slab_t, n_local), dtype=torch.int32).pin_memory() for _ in range(3)]
+
+    def slabs():
+        for i in range(ENV_T // slab_t):
+            yield ring[i % len(ring)]
+
+    e2e_io = {}
+
+    def env_e2e_pass():
+        out = env.rollout_stream(slabs())
+        e2e_io["h2d"], e2e_io["d2h"] = out["h2d_bytes"], out["d2h_bytes"]
+
+    env_e2e_pass()
+    k_e2e = max(1, min(K, 3))
+    t_env_e2e = timed(env_e2e_pass, k_e2e)
+    env_e2e_value = float(ENV_TOTAL) * ENV_T * k_e2e / t_env_e2e
+    del ring, actions
+    torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ cfg 3 (rank 0, extra)
+    cfg3 = None
+    if rank == 0:
+        lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
+        env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
+        a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev, generator=gen)
+        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
+        for _ in range(W):
+            env3.rollout(a3, per_env=True)
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(K):
+            flush.fill_(1)                            # 256 MB write: flush the 126 MB L2 between passes
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            env3.rollout(a3, per_env=True)
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / 1000.0)
+        t3 = float(np.mean(times))
+        cfg3 = {"workload": "cfg3: 65,536 16x16 envs, T=1024, per-env levels, 1 GPU, L2 flushed between passes",
+                "value": CFG3_N * CFG3_T / t3, "unit": "steps/s", "ms_per_pass": 1000 * t3,
+                "roofline_frac": BYTES_PER_STEP_SUMMARY * CFG3_N * CFG3_T / t3 / 1e9 / peak}
+        del env3, a3, lv3, flush
+        torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ VI workload (cfg 5)
+    r0, r1 = shard_rows(VI_SIZE, world, rank)
+    grid = synth.maze_plan_grid(VI_SIZE, VI_SIZE, seed=0, dtype=np.float32, device=dev, row_begin=r0, row_end=r1)
+    pl = Planner(None, np.float32, dev, grid=grid)
+    if world == 1:
+        class _Solo(ShardedValueIteration):          # same driver, no process group needed
+            def __init__(self, planner):
+                self.pl, self.group, self.rank, self.world, self.collectives = planner, None, 0, 1, 0
+        svi = _Solo(pl)
+    else:
+        svi = ShardedValueIteration(pl)
+    vi_meta = {}
+
+    def vi_pass():
+        v, tie, sweeps, last = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=8)
+        vi_meta["sweeps"], vi_meta["last"] = sweeps, last
+
+    vi_pass()                                          # warm-up solve (also fixes the sweep count)
+    k_vi = max(1, min(K, 3))
+    pl.launches = 0
+    svi.collectives = 0
+    t_vi = timed(vi_pass, k_vi)
+    vi_launches, vi_colls = pl.launches, svi.collectives
+    sweeps = vi_meta["sweeps"]
+    cells = float(VI_SIZE) * VI_SIZE
+    vi_value = sweeps * cells * k_vi / t_vi
+    # dominant kernel alone: fused-greedy sweeps back to back, CUDA events, no convergence logic
+    a, b = grid.empty(), grid.empty()
+    for _ in range(3):
+        pl.sweep(a, b, 3, None, VI_GAMMA)
+    n_sw = 20
+    t_sw = timed(lambda: pl.sweep(a, b, 3, None, VI_GAMMA), n_sw) / n_sw
+    vi_achieved = BYTES_PER_CELL_FUSED_F32 * (r1 - r0) * VI_SIZE / t_sw / 1e9
+    del a, b
+    # e2e: V0 from pinned host memory, V and tie masks back to pinned host memory
+    rows = r1 - r0
+    v0_h = torch.zeros((rows, VI_SIZE), dtype=torch.float32).pin_memory()
+    v_h = torch.empty((rows, VI_SIZE), dtype=torch.float32).pin_memory()
+    tie_h = torch.empty((rows, VI_SIZE), dtype=torch.uint8).pin_memory()
+    io = {}
+
+    def vi_e2e_pass():
+        s, last, h2d, d2h = svi.solve_host(v0_h, v_h, tie_h, "uniform", threshold=VI_THETA, max_steps=1000,
+                                           discount_factor=VI_GAMMA, chunk=8)
+        io["h2d"], io["d2h"], io["sweeps"] = h2d, d2h, s
+
+    t_vi_e2e = timed(vi_e2e_pass, 1)
+    vi_e2e_value = io["sweeps"] * cells / t_vi_e2e
+    clocks = sampler.stop() if sampler else None
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
+    cpu_env = cpu_vi = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import cpu_baseline as cb
+        procs = os.cpu_count() or 1
+        r = cb.env_steps_per_sec(ENV_SHAPE[0], ENV_SHAPE[1], 32768, 64, procs)
+        cpu_env = {"value": r["value"], "unit": "steps/s", "cores": procs, "kind": "port",
+                   "sample": "%d procs x 32768 8x8 envs x 64 steps, oracle NumPy port, same generator" % procs}
+        r = cb.vi_cell_updates_per_sec(512, 512, 4, procs, dtype=np.float32)
+        cpu_vi = {"value": r["value"], "unit": "cell-updates/s", "cores": procs, "kind": "port",
+                  "sample": "%d replicas of a 512x512 synthetic maze x 4 sweep+greedy iterations, fp32 oracle" % procs}
+
+    if rank == 0:
+        line = {
+            "metric": "env_steps_per_sec", "value": env_value, "unit": "steps/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": 1000.0 * t_env / K, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": env_config(world),
+            "roofline": {"bound": "hbm", "achieved": env_achieved, "peak": peak, "unit": "GB/s",
+                         "frac": env_achieved / peak, "traffic": profiled_traffic("rollout_cfg4"),
+                         "kernel": "rollout (gu_rollout), 4 B/step x %d envs x %d steps per launch" % (n_local, ENV_T),
+                         "peak_source": peak_src},
+            "e2e": {"value": env_e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_io["h2d"] * world,
+                    "d2h_bytes_per_step": e2e_io["d2h"] * world,
+                    "note": "pinned host action slabs [16, N] streamed H2D on a side stream, summaries D2H"},
+            "gpu_launches": env_launches,
+            "cpu_baseline": cpu_env,
+            "clocks": clocks,
+            "vi": {
+                "metric": "vi_cell_updates_per_sec", "value": vi_value, "unit": "cell-updates/s",
+                "dtype": "f32", "sweeps_per_solve": sweeps, "ms_per_solve": 1000.0 * t_vi / k_vi,
+                "solves_timed": k_vi, "scaling": "strong",
+                "config": {"workload": "cfg5: value iteration on a 16384x16384 synthetic maze, gamma 0.9, "
+                                       "theta 1e-6, uniform policy0, V0=0",
+                           "parallelism": "row-sharded x%d, halo send/recv + residual MAX all-reduce per sweep" % world,
+                           "l2": "inputs larger than L2 (%.2f GB of V per GPU)" % ((r1 - r0) * VI_SIZE * 4 / 1e9)},
+                "roofline": {"bound": "hbm", "achieved": vi_achieved, "peak": peak, "unit": "GB/s",
+                             "frac": vi_achieved / peak, "traffic": profiled_traffic("sweep_greedy_f32_cfg5"),
+                             "kernel": "fused-greedy sweep (gu_sweep_f32, GU_POLICY_GREEDY), 8.375 B/cell",
+                             "ms_per_launch": 1000.0 * t_sw, "peak_source": peak_src},
+                "e2e": {"value": vi_e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": io["h2d"] * world,
+                        "d2h_bytes_per_step": io["d2h"] * world},
+                "gpu_launches": vi_launches, "collectives": vi_colls, "cpu_baseline": cpu_vi,
+            },
+            "cfg3": cfg3,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -14,6 +14,7 @@ c_ptr = ctypes.c_void_p
 
 GU_FLAG_AUTO_RESET = 1
 GU_FLAG_NO_CARE_TERMINAL = 2
+GU_FLAG_ACCUMULATE = 4
 GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
 
 EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",

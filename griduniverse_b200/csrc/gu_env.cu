@@ -157,8 +157,9 @@ rollout_generic_kernel(LevelsView lv, int64_t T, const int32_t* __restrict__ act
       dcnt += d ? 1 : 0;
     }
     pos[i] = s;
-    if (env_return) env_return[i] = static_cast<int32_t>(rsum);
-    if (env_done) env_done[i] = static_cast<int32_t>(dcnt);
+    const bool acc = flags & GU_FLAG_ACCUMULATE;
+    if (env_return) env_return[i] = static_cast<int32_t>(rsum) + (acc ? env_return[i] : 0);
+    if (env_done) env_done[i] = static_cast<int32_t>(dcnt) + (acc ? env_done[i] : 0);
   }
   publish_stats(rsum, dcnt, stats);
 }

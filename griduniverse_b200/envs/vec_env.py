@@ -163,6 +163,7 @@ class GridUniverseVecEnv(object):
                                   _cabi.ptr(env_done), _cabi.ptr(self.stats), _cabi.ptr(self.levels.tables),
                                   self._flags(), _cabi.stream_ptr())
         _cabi.check("gu_rollout", rc)
+        self.launches = getattr(self, "launches", 0) + 1
         out = {"pos": self.pos, "env_return": env_ret, "env_done": env_done, "stats": self.stats,
                "obs": obs, "reward": reward, "done": done}
         if not host:
@@ -177,6 +178,55 @@ class GridUniverseVecEnv(object):
             res[k] = h
         torch.cuda.current_stream().synchronize()
         return {k: (None if v is None else v.numpy().copy()) for k, v in res.items()}
+
+    def rollout_stream(self, slabs):
+        """Streamed rollout from HOST memory: ``slabs`` is an iterable of pinned int32 host
+        tensors [t_i, N] (consecutive time slices of the action stream).  Each slab is copied
+        host->device on a side stream into one of two device buffers while the kernel works on
+        the previous slab; per-env returns / done counts accumulate across slabs.  Returns NumPy
+        ``pos``, ``env_return``, ``env_done`` and ``stats`` (device->host through pinned memory)."""
+        n = self.num_envs
+        main = torch.cuda.current_stream()
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+            self._slab_bufs = [None, None]
+        copy = self._copy_stream
+        ready = [torch.cuda.Event(), torch.cuda.Event()]
+        free = [torch.cuda.Event(), torch.cuda.Event()]
+        env_ret = torch.zeros(n, dtype=torch.int32, device=self.device)
+        env_done = torch.zeros(n, dtype=torch.int32, device=self.device)
+        copy.wait_stream(main)
+        h2d = 0
+        for i, slab in enumerate(slabs):
+            assert slab.dtype == torch.int32 and slab.dim() == 2 and slab.shape[1] == n
+            b, t = i % 2, int(slab.shape[0])
+            buf = self._slab_bufs[b]
+            if buf is None or buf.shape[0] < t:
+                buf = self._slab_bufs[b] = torch.empty((t, n), dtype=torch.int32, device=self.device)
+            with torch.cuda.stream(copy):
+                if i >= 2:
+                    copy.wait_event(free[b])
+                buf[:t].copy_(slab, non_blocking=True)
+                ready[b].record(copy)
+            h2d += slab.numel() * 4
+            main.wait_event(ready[b])
+            rc = self._lib.gu_rollout(self.levels.ref(), n, t, _cabi.ptr(buf), _cabi.ptr(self.pos), None, None,
+                                      None, None, _cabi.ptr(env_ret), _cabi.ptr(env_done), _cabi.ptr(self.stats),
+                                      _cabi.ptr(self.levels.tables), self._flags() | _cabi.GU_FLAG_ACCUMULATE,
+                                      _cabi.stream_ptr(main))
+            _cabi.check("gu_rollout", rc)
+            free[b].record(main)
+            self.launches = getattr(self, "launches", 0) + 1
+        out = {}
+        for k, v in (("pos", self.pos), ("env_return", env_ret), ("env_done", env_done), ("stats", self.stats)):
+            h = self._pin("stream_" + k, tuple(v.shape), v.dtype)
+            h.copy_(v, non_blocking=True)
+            out[k] = h
+        main.synchronize()
+        res = {k: v.numpy() for k, v in out.items()}
+        res["h2d_bytes"] = h2d
+        res["d2h_bytes"] = sum(v.numel() * v.element_size() for v in out.values())
+        return res
 
     def look_step_ahead(self, states, actions, care_about_terminal=True):
         """Batched look_step_ahead (griduniverse_env.py:136-155) -> (next, reward, terminal).

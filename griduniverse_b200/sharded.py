@@ -1,0 +1,131 @@
+"""Row-sharded value iteration across GPUs (one process per GPU, torch.distributed).
+
+One value grid is split into contiguous row blocks; every rank owns rows
+[row_begin, row_end) plus one ghost row above and below.  Per sweep the ranks exchange
+their boundary rows with both neighbours (send/recv, NCCL over NVLink) and combine the
+signed residual max(V - V') with a MAX all-reduce; everything is stream-ordered, the host
+only reads a chunk of residuals every `chunk` sweeps.  The sweep kernels after the converged
+one are gated off on the device (see gu_sweep_* in include/gu_b200.h), so every rank stops
+on the same sweep and the result is bit-identical to the single-GPU run.
+
+Env batches need none of this: they shard by env range with no collective.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+
+
+def shard_rows(Y, world, rank):
+    """Contiguous, balanced row blocks: rank r owns [r*Y//world, (r+1)*Y//world)."""
+    return (rank * Y) // world, ((rank + 1) * Y) // world
+
+
+def shard_envs(n_envs, world, rank):
+    """Contiguous env ranges for the batched-env workloads (no collective needed)."""
+    return (rank * n_envs) // world, ((rank + 1) * n_envs) // world
+
+
+class ShardedValueIteration(object):
+    """Drives a per-rank ``Planner`` (rows of one grid) with halo exchange + residual all-reduce.
+
+    ``planner`` is duck-typed: it needs ``grid`` (rows, pitch, empty(), dense()), ``sweep``,
+    ``greedy``, ``new_residuals``, ``stage_policy``, ``stage_value`` and ``np_dtype`` -- the
+    CUDA ``Planner`` in production, a CPU stand-in in the gloo tests of the host logic."""
+
+    def __init__(self, planner, group=None):
+        self.pl = planner
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        g = planner.grid
+        assert shard_rows(g.Y, self.world, self.rank) == (g.row_begin, g.row_end), \
+            "planner rows do not match this rank's shard"
+        self.collectives = 0
+
+    # ------------------------------------------------------------------ communication
+    def exchange_halos(self, v):
+        """Fill the ghost rows of padded ``v`` from the neighbours' boundary rows."""
+        ops = []
+        up, down = self.rank - 1, self.rank + 1
+        if up >= 0:
+            ops.append(dist.P2POp(dist.isend, v[1], self._global(up), self.group))
+            ops.append(dist.P2POp(dist.irecv, v[0], self._global(up), self.group))
+        if down < self.world:
+            ops.append(dist.P2POp(dist.isend, v[-2], self._global(down), self.group))
+            ops.append(dist.P2POp(dist.irecv, v[-1], self._global(down), self.group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
+            self.collectives += 1
+
+    def _global(self, group_rank):
+        return group_rank if self.group is None else dist.get_global_rank(self.group, group_rank)
+
+    def allreduce_max(self, t):
+        if self.world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX, group=self.group)
+            self.collectives += 1
+
+    # ------------------------------------------------------------------ value iteration
+    def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
+                        discount_factor=1.0, chunk=8):
+        """dynamic_programming.py:8-28 on the sharded grid.
+        Returns (V_padded_shard, tie_masks_padded_shard, sweeps, last_delta)."""
+        pl = self.pl
+        kind0, pol_t = pl.stage_policy(policy)
+        thr = pl.np_dtype.type(threshold)
+        bufs = [pl.stage_value(value_function), pl.grid.empty()]
+        res = pl.new_residuals(max(max_steps, 1))
+        k, sweeps, last = 0, 0, float("nan")
+        converged = False
+        while k < max_steps and not converged:
+            n = min(chunk, max_steps - k)
+            for _ in range(n):
+                self.exchange_halos(bufs[k % 2])
+                pl.sweep(bufs[k % 2], bufs[(k + 1) % 2], kind0 if k == 0 else _cabi.GU_POLICY_GREEDY,
+                         pol_t if k == 0 else None, discount_factor, res[k:k + 1],
+                         res[k - 1:k] if k > 0 else None, threshold)
+                self.allreduce_max(res[k:k + 1])
+                k += 1
+            r = res[k - n:k].cpu().numpy()
+            hit = np.flatnonzero(r < thr)
+            if hit.size:
+                sweeps = k - n + int(hit[0]) + 1
+                last = float(r[hit[0]])
+                converged = True
+            else:
+                sweeps, last = k, float(r[-1])
+        v = bufs[sweeps % 2]
+        self.exchange_halos(v)               # greedy needs the neighbours' rows of the final V
+        tie = pl.greedy(v, discount_factor)
+        return v, tie, sweeps, last
+
+    def solve_host(self, v0_host, v_out_host, tie_out_host, policy="uniform", **kw):
+        """End-to-end solve with HOST buffers (pinned torch tensors holding this rank's owned
+        rows, dense [rows, X]): host->device copy of the initial value function, the sharded
+        value iteration, device->host copy of V and of the greedy tie masks.
+        Returns (sweeps, last_delta, h2d_bytes, d2h_bytes)."""
+        g = self.pl.grid
+        v0 = g.empty()
+        v0[1:-1, :g.X].copy_(v0_host.view(g.rows, g.X), non_blocking=True)
+        v, tie, sweeps, last = self.value_iteration(policy, v0, **kw)
+        v_out_host.view(g.rows, g.X).copy_(v[1:-1, :g.X], non_blocking=True)
+        tie_out_host.view(g.rows, g.X).copy_(tie[1:-1, :g.X], non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        h2d = v0_host.numel() * v0_host.element_size()
+        d2h = v_out_host.numel() * v_out_host.element_size() + tie_out_host.numel()
+        return sweeps, last, h2d, d2h
+
+    def gather_dense(self, padded):
+        """All ranks' owned rows concatenated (for tests / small grids)."""
+        g = self.pl.grid
+        local = g.dense(padded).contiguous()
+        sizes = [(shard_rows(g.Y, self.world, r)[1] - shard_rows(g.Y, self.world, r)[0]) * g.X
+                 for r in range(self.world)]
+        buf = torch.zeros(max(sizes), dtype=local.dtype, device=local.device)
+        buf[:local.numel()] = local
+        outs = [torch.empty_like(buf) for _ in sizes]
+        dist.all_gather(outs, buf, group=self.group)
+        return torch.cat([o[:s] for o, s in zip(outs, sizes)])

@@ -56,6 +56,7 @@ typedef struct {
 
 #define GU_FLAG_AUTO_RESET 1u      /* after a done step the env continues from its start state */
 #define GU_FLAG_NO_CARE_TERMINAL 2u /* care_about_terminal=False (griduniverse_env.py:150-153) */
+#define GU_FLAG_ACCUMULATE 4u      /* gu_rollout: env_return / env_done += instead of = (streamed slabs) */
 
 /* One step for N envs: GridUniverseEnv._step (griduniverse_env.py:176-185) =
  * look_step_ahead(current_state, action) (:136-155) for every env.

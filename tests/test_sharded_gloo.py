@@ -1,0 +1,128 @@
+"""Host logic of the row-sharded value iteration under world_size 2 and 3 on CPU (gloo):
+row partition, ghost-row exchange, residual MAX all-reduce, device-style gating and the
+chunked convergence check.  The per-rank sweep is the ORACLE restricted to the shard's rows
+(the CUDA sweep itself is covered by the -m gpu tests), so the sharded result must be
+bit-identical to the oracle's whole-grid value iteration."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from oracle import gu_oracle as orc
+from griduniverse_b200 import _cabi, synth
+from griduniverse_b200.sharded import ShardedValueIteration, shard_envs, shard_rows
+
+
+class _Grid(object):
+    def __init__(self, X, Y, r0, r1):
+        self.X, self.Y, self.row_begin, self.row_end = X, Y, r0, r1
+        self.rows, self.pitch = r1 - r0, X
+
+    def empty(self, dtype=torch.float64):
+        return torch.zeros((self.rows + 2, self.pitch), dtype=dtype)
+
+    def dense(self, padded):
+        return padded[1:-1, :self.X].reshape(-1)
+
+
+class OraclePlanner(object):
+    """CPU stand-in with the Planner interface ShardedValueIteration uses."""
+
+    def __init__(self, wall, goal, lava, X, Y, r0, r1):
+        self.grid = _Grid(X, Y, r0, r1)
+        self.np_dtype = np.dtype(np.float64)
+        lo, hi = max(r0 - 1, 0), min(r1 + 1, Y)
+        self.lo, self.hi = lo, hi
+        self.sub = orc.Level.from_masks(X, hi - lo, wall[lo:hi], goal[lo:hi], lava[lo:hi])
+        self.nxt = orc.next_table(self.sub)
+        self.own = slice((r0 - lo) * X, (r1 - lo) * X)
+        self.sweeps_run = 0
+
+    def _sub_values(self, v):
+        g = self.grid
+        first = self.lo - (g.row_begin - 1)
+        return v[first:first + (self.hi - self.lo)].reshape(-1).numpy()
+
+    def stage_policy(self, policy):
+        assert policy == "uniform"
+        return _cabi.GU_POLICY_UNIFORM, None
+
+    def stage_value(self, value_function):
+        return self.grid.empty()
+
+    def new_residuals(self, n):
+        return torch.full((n,), float("-inf"), dtype=torch.float64)
+
+    def _policy(self, kind, vs):
+        if kind == _cabi.GU_POLICY_UNIFORM:
+            return np.full((self.sub.N, 4), 0.25)
+        return orc.masks_to_policy(orc.greedy_masks(self.sub, vs, self.gamma, nxt=self.nxt))
+
+    def sweep(self, v_in, v_out, kind, pol_t, gamma, residual=None, gate=None, threshold=0.0):
+        if gate is not None and gate.item() < threshold:
+            return
+        self.gamma = gamma
+        vs = self._sub_values(v_in)
+        new = orc.sweep(self.sub, self._policy(kind, vs), vs, gamma, nxt=self.nxt)
+        v_out[1:-1] = torch.from_numpy(new[self.own].reshape(self.grid.rows, self.grid.X))
+        if residual is not None:
+            residual[0] = max(residual[0].item(), float(np.max(vs[self.own] - new[self.own])))
+        self.sweeps_run += 1
+
+    def greedy(self, v, gamma):
+        m = orc.greedy_masks(self.sub, self._sub_values(v), gamma, nxt=self.nxt)
+        out = self.grid.empty(torch.uint8)
+        out[1:-1] = torch.from_numpy(m[self.own].reshape(self.grid.rows, self.grid.X))
+        return out
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, X, Y, chunk, out_dir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        wall, goal, lava = synth.maze_numpy(X, Y, seed=2)
+        r0, r1 = shard_rows(Y, world, rank)
+        pl = OraclePlanner(wall, goal, lava, X, Y, r0, r1)
+        svi = ShardedValueIteration(pl)
+        v, tie, sweeps, last = svi.value_iteration("uniform", None, 1e-6, 1000, 0.9, chunk=chunk)
+        V = svi.gather_dense(v).numpy()
+        M = svi.gather_dense(tie).numpy()
+        if rank == 0:
+            np.savez(os.path.join(out_dir, "out.npz"), V=V, M=M, sweeps=sweeps, ran=pl.sweeps_run)
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,chunk", [(2, 8), (3, 5)])
+def test_sharded_value_iteration_matches_whole_grid(tmp_path, world, chunk):
+    X, Y = 24, 30
+    mp.spawn(_worker, args=(world, _free_port(), X, Y, chunk, str(tmp_path)), nprocs=world, join=True)
+    out = np.load(os.path.join(str(tmp_path), "out.npz"))
+    wall, goal, lava = synth.maze_numpy(X, Y, seed=2)
+    olv = orc.Level.from_masks(X, Y, wall, goal, lava)
+    V, P, sweeps = orc.value_iteration(np.ones((olv.N, 4)) / 4, olv, None, 1e-6, 1000, 0.9)
+    assert int(out["sweeps"]) == sweeps
+    assert int(out["ran"]) == sweeps           # sweeps after convergence were gated off
+    assert out["V"].tobytes() == V.tobytes()
+    assert np.array_equal(out["M"], orc.policy_to_masks(P))
+
+
+def test_partitions_cover_everything():
+    for total, world in ((16384, 8), (30, 4), (7, 3), (16777216, 8)):
+        rows = [shard_rows(total, world, r) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == total
+        assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+        assert [shard_envs(total, world, r) for r in range(world)] == rows
