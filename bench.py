@@ -370,6 +370,39 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_profile(args):
+    """Short run for ncu (never a bench number): 2 rollout passes of the cfg-4 shape, a few sweeps
+    of each kind and one greedy extraction on the cfg-5 grid."""
+    import torch
+    from griduniverse_b200 import synth
+    from griduniverse_b200.envs import GridUniverseVecEnv
+    from griduniverse_b200.planner import Planner
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n = ENV_TOTAL // args.profile_div
+    levels = synth.env_levels_device(ENV_SHAPE[0], ENV_SHAPE[1], n, seed=0, device=dev)
+    env = GridUniverseVecEnv(n, levels=levels, auto_reset=True, device=dev)
+    actions = torch.randint(0, 4, (ENV_T, n), dtype=torch.int32, device=dev)
+    for _ in range(2):
+        env.rollout(actions, trajectories=False, per_env=True)
+    env.step(actions[0])
+    del actions
+    size = VI_SIZE // max(1, int(args.profile_div ** 0.5) // 2 * 2 or 1)
+    for dt in (np.float32, np.float64):
+        grid = synth.maze_plan_grid(size, size, seed=0, dtype=dt, device=dev)
+        pl = Planner(None, dt, dev, grid=grid)
+        a, b = grid.empty(), grid.empty()
+        res = pl.new_residuals(4)
+        pl.sweep(a, b, 2, None, VI_GAMMA, res[0:1])
+        for i in range(3):
+            pl.sweep(b if i % 2 == 0 else a, a if i % 2 == 0 else b, 3, None, VI_GAMMA, res[i + 1:i + 2])
+        tie = pl.greedy(a, VI_GAMMA)
+        pl.sweep(a, b, 1, tie, VI_GAMMA)
+        del a, b, tie, pl, grid
+    torch.cuda.synchronize()
+    print("profile run done")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
@@ -377,8 +410,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true", help="short kernel sequence for ncu")
+    ap.add_argument("--profile-div", type=int, default=1, help="shrink the profile workloads by this factor")
     args = ap.parse_args()
-    if args.impl == "reference":
+    if args.profile:
+        run_profile(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_ours(args)

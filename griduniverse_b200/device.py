@@ -111,8 +111,16 @@ class PlanGrid(object):
             planes.append(_words_tensor(pack_grid_plane(m.reshape(self.Y, self.X), self.row_begin, self.row_end,
                                                         self.pitch_words), self.device))
         self.wall, self.goal, self.lava = planes
+        self.finish()
+
+    def finish(self):
+        """Build the descriptor and the derived `info` plane (gu_pack_info) the tiled kernels read."""
         self.desc = _cabi.GuGrid(self.X, self.Y, self.row_begin, self.row_end, self.pitch, self.pitch_words,
-                                 self.wall.data_ptr(), self.goal.data_ptr(), self.lava.data_ptr())
+                                 self.wall.data_ptr(), self.goal.data_ptr(), self.lava.data_ptr(), None)
+        self.info = torch.empty((self.rows + 2) * self.pitch, dtype=torch.uint8, device=self.device)
+        rc = _cabi.lib().gu_pack_info(ctypes.byref(self.desc), _cabi.ptr(self.info), _cabi.stream_ptr())
+        _cabi.check("gu_pack_info", rc)
+        self.desc.info = self.info.data_ptr()
 
     def ref(self):
         return ctypes.byref(self.desc)

@@ -146,6 +146,5 @@ def maze_plan_grid(X, Y, seed=0, dtype=np.float32, device="cuda", row_begin=0, r
     rc = _cabi.lib().gu_synth_maze(X, Y, g.row_begin, g.row_end, g.pitch_words, seed, _cabi.ptr(g.wall),
                                    _cabi.ptr(g.goal), _cabi.ptr(g.lava), _cabi.stream_ptr())
     _cabi.check("gu_synth_maze", rc)
-    g.desc = _cabi.GuGrid(X, Y, g.row_begin, g.row_end, g.pitch, g.pitch_words, g.wall.data_ptr(),
-                          g.goal.data_ptr(), g.lava.data_ptr())
+    g.finish()
     return g

@@ -143,7 +143,12 @@ int gu_look_step_ahead(const gu_levels* lv, int64_t m, const int32_t* states, co
  * row the ghost row below (filled by the halo exchange; never read at the true
  * grid edges).  The bit planes hold the same rows with `pitch_words` uint32 per
  * row, bit (x & 31) of word (x >> 5); bits at x >= X are zero.
- * pitch >= X; for the tiled kernels pitch*sizeof(T) % 16 == 0. */
+ * pitch >= X.
+ * `info` (optional, may be NULL): derived per-cell byte plane built once per level by
+ * gu_pack_info, same padded layout as the per-cell arrays: bits 0-3 = action a is blocked
+ * (grid edge | wall at the target | cell terminal), bit 4 goal, bit 5 lava.  With it, and
+ * with pitch % 4 == 0, pitch*sizeof(T) % 16 == 0 and 16-byte aligned arrays, the sweep /
+ * greedy entry points run the register-tiled kernels; otherwise the layout-agnostic ones. */
 typedef struct {
   int32_t X, Y;
   int32_t row_begin, row_end;
@@ -152,7 +157,11 @@ typedef struct {
   const uint32_t* wall;
   const uint32_t* goal;
   const uint32_t* lava;
+  const uint8_t* info;
 } gu_grid;
+
+/* Build the `info` plane (uint8[(rows+2)*pitch]) of a grid / shard from its bit planes. */
+int gu_pack_info(const gu_grid* g, uint8_t* info, void* stream);
 
 #define GU_POLICY_PROBS 0   /* policy = T[cells][4] probabilities (any stochastic policy) */
 #define GU_POLICY_MASK 1    /* policy = uint8[cells] tie masks: prob 1/popcount on set bits */
