@@ -20,15 +20,13 @@
 namespace gu {
 
 template <typename T> struct Vec;
-template <> struct Vec<float> { using type = float4; static constexpr int CPT = 4; };
-template <> struct Vec<double> { using type = double2; static constexpr int CPT = 2; };
+template <> struct Vec<float> { using type = float4; static constexpr int W = 4; };
+template <> struct Vec<double> { using type = double2; static constexpr int W = 2; };
 
-template <typename T> __device__ __forceinline__ void unpack(const float4& v, T (&o)[4]) {
-  o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
-}
-__device__ __forceinline__ void unpack(const double2& v, double (&o)[2]) { o[0] = v.x; o[1] = v.y; }
-__device__ __forceinline__ float4 pack(const float (&o)[4]) { return make_float4(o[0], o[1], o[2], o[3]); }
-__device__ __forceinline__ double2 pack(const double (&o)[2]) { return make_double2(o[0], o[1]); }
+__device__ __forceinline__ void unpack(const float4& v, float* o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+__device__ __forceinline__ void unpack(const double2& v, double* o) { o[0] = v.x; o[1] = v.y; }
+__device__ __forceinline__ float4 pack(const float* o) { return make_float4(o[0], o[1], o[2], o[3]); }
+__device__ __forceinline__ double2 pack(const double* o) { return make_double2(o[0], o[1]); }
 
 template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -40,41 +38,122 @@ __device__ __forceinline__ double reward_f(uint32_t info, double) {
   return (info & 0x20u) ? -10.0 : ((info & 0x10u) ? 10.0 : -1.0);
 }
 
+// Bellman backup of one cell for a policy that is uniform on the tie set:
+//   acc = R[s];  for a in 0..3: if tie_a: acc = acc + p * g_a     (utils.py:23-26, left to right)
+// with tie_a = (r_a == m) && live and p = inv_cnt[#ties].  Written in PTX so the four
+// compares feed predicated mul/add pairs directly (no mask round trip through registers).
+__device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], float m, bool live,
+                                             const float (&ga)[4], const float* inv_cnt_smem) {
+  float acc;
+  const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(inv_cnt_smem));
+  asm("{\n\t"
+      ".reg .pred t0, t1, t2, t3, lv;\n\t"
+      ".reg .u32 c, a;\n\t"
+      ".reg .f32 p, x;\n\t"
+      "setp.ne.u32 lv, %11, 0;\n\t"
+      "setp.eq.and.f32 t0, %2, %6, lv;\n\t"
+      "setp.eq.and.f32 t1, %3, %6, lv;\n\t"
+      "setp.eq.and.f32 t2, %4, %6, lv;\n\t"
+      "setp.eq.and.f32 t3, %5, %6, lv;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "@t0 add.u32 c, c, 4;\n\t"
+      "@t1 add.u32 c, c, 4;\n\t"
+      "@t2 add.u32 c, c, 4;\n\t"
+      "@t3 add.u32 c, c, 4;\n\t"
+      "add.u32 a, c, %12;\n\t"
+      "ld.shared.f32 p, [a];\n\t"
+      "mov.f32 %0, %1;\n\t"
+      "mul.rn.f32 x, p, %7;\n\t"
+      "@t0 add.rn.f32 %0, %0, x;\n\t"
+      "mul.rn.f32 x, p, %8;\n\t"
+      "@t1 add.rn.f32 %0, %0, x;\n\t"
+      "mul.rn.f32 x, p, %9;\n\t"
+      "@t2 add.rn.f32 %0, %0, x;\n\t"
+      "mul.rn.f32 x, p, %10;\n\t"
+      "@t3 add.rn.f32 %0, %0, x;\n\t"
+      "}"
+      : "=&f"(acc)
+      : "f"(rs), "f"(ra[0]), "f"(ra[1]), "f"(ra[2]), "f"(ra[3]), "f"(m), "f"(ga[0]), "f"(ga[1]), "f"(ga[2]),
+        "f"(ga[3]), "r"(static_cast<uint32_t>(live)), "r"(lut));
+  return acc;
+}
+__device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, bool live,
+                                              const double (&ga)[4], const double* inv_cnt_smem) {
+  double acc;
+  const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(inv_cnt_smem));
+  asm("{\n\t"
+      ".reg .pred t0, t1, t2, t3, lv;\n\t"
+      ".reg .u32 c, a;\n\t"
+      ".reg .f64 p, x;\n\t"
+      "setp.ne.u32 lv, %11, 0;\n\t"
+      "setp.eq.and.f64 t0, %2, %6, lv;\n\t"
+      "setp.eq.and.f64 t1, %3, %6, lv;\n\t"
+      "setp.eq.and.f64 t2, %4, %6, lv;\n\t"
+      "setp.eq.and.f64 t3, %5, %6, lv;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "@t0 add.u32 c, c, 8;\n\t"
+      "@t1 add.u32 c, c, 8;\n\t"
+      "@t2 add.u32 c, c, 8;\n\t"
+      "@t3 add.u32 c, c, 8;\n\t"
+      "add.u32 a, c, %12;\n\t"
+      "ld.shared.f64 p, [a];\n\t"
+      "mov.f64 %0, %1;\n\t"
+      "mul.rn.f64 x, p, %7;\n\t"
+      "@t0 add.rn.f64 %0, %0, x;\n\t"
+      "mul.rn.f64 x, p, %8;\n\t"
+      "@t1 add.rn.f64 %0, %0, x;\n\t"
+      "mul.rn.f64 x, p, %9;\n\t"
+      "@t2 add.rn.f64 %0, %0, x;\n\t"
+      "mul.rn.f64 x, p, %10;\n\t"
+      "@t3 add.rn.f64 %0, %0, x;\n\t"
+      "}"
+      : "=&d"(acc)
+      : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
+        "d"(ga[3]), "r"(static_cast<uint32_t>(live)), "r"(lut));
+  return acc;
+}
+
 constexpr int kTiledWarps = 4;
 
-// One row of the sliding window: discounted values and rounded q-values of the thread's own
-// columns plus the left / right neighbour columns, the raw V (for the residual) and info bytes.
+// One row of the sliding window: discounted values and rounded scaled q-values of the thread's
+// own columns plus the left / right neighbour columns, the raw V (for the residual), info bytes.
 template <typename T, int CPT, bool TIES>
 struct WinRow {
   T g[CPT], gl, gr;
   T rt[TIES ? CPT : 1], rtl, rtr;
   T v[CPT];
-  uint32_t info;   // CPT info bytes, little-endian
+  uint32_t info[CPT / 4 ? CPT / 4 : 1];   // CPT info bytes, little-endian
 };
 
-template <typename T, bool TIES>
-__device__ __forceinline__ void cell_terms(T v, uint32_t info, T gamma, T& g, T& rt) {
-  using N = Num<T>;
-  g = N::mul(gamma, v);
-  if (TIES) {
-    const T t = N::mul(N::add(reward_f(info, T(0)), g), N::scale());
-    // rint(): the magic-number add is exact below 2^22 (f32) / 2^51 (f64); rare slow path above
-    rt = N::add(N::add(t, N::magic()), -N::magic());
-    if (!(N::abs(t) < N::magic_limit())) rt = N::rnd(t);
-  }
+template <int CPT>
+__device__ __forceinline__ uint32_t info_of(const uint32_t* info, int j) {
+  return (info[j >> 2] >> (8 * (j & 3))) & 0xffu;
 }
 
-template <typename T, int KIND, bool WRITE_TIE>
+// rint(t) for t = q * 1e8.  f32: |t| >= 2^23 is already integral (the common case: |q| > 0.084).
+// f64: the magic-number add is exact below 2^51.  `need_slow` collects the rare other cases.
+__device__ __forceinline__ float round_fast(float t, bool& need_slow) {
+  need_slow |= fabsf(t) < 8388608.0f;
+  return t;
+}
+__device__ __forceinline__ double round_fast(double t, bool& need_slow) {
+  need_slow |= !(fabs(t) < 2251799813685248.0);
+  return __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+}
+
+template <typename T, int KIND, bool WRITE_TIE, int NV>
 __global__ void __launch_bounds__(kTiledWarps * 32)
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
                    T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block) {
   using N = Num<T>;
   using V = typename Vec<T>::type;
-  constexpr int CPT = Vec<T>::CPT;
+  constexpr int W = Vec<T>::W;
+  constexpr int CPT = W * NV;                 // cells per thread: NV 16-byte vectors
+  constexpr int IW = CPT / 4 ? CPT / 4 : 1;   // 32-bit words of info per thread-row
   constexpr bool TIES = (KIND == GU_POLICY_GREEDY) || WRITE_TIE;
   __shared__ T scratch[kTiledWarps];
-  __shared__ T inv_cnt[8];                 // 1/len(ties): exact 1, 1/2, 1/3 (correctly rounded), 1/4
+  __shared__ T inv_cnt[8];                    // 1/len(ties): exact 1, 1/2, 1/3 (correctly rounded), 1/4
   if (gate != nullptr && *gate < gate_thr) return;
   if (threadIdx.x < 8) inv_cnt[threadIdx.x] = N::inv(threadIdx.x);
   __syncthreads();
@@ -87,33 +166,57 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const bool active = x0 < g.X;                       // lanes past the grid still take part in shuffles
   const bool has_l = active && lane == 0 && x0 > 0;   // edge lanes fetch one halo column each
   const bool has_r = active && lane == 31 && x0 + CPT < g.X;
+  const bool full = x0 + CPT <= g.X;
   const size_t pitch = g.pitch;
+  const int hoff = has_l ? -1 : CPT;                  // halo column relative to x0
 
   WinRow<T, CPT, TIES> w[3];
+  struct RawRow { V v[NV]; uint32_t info[IW]; T hv; uint32_t hinfo; } raw;
 
-  auto load_row = [&](int ar, WinRow<T, CPT, TIES>& r) {
+  auto issue_loads = [&](int ar) {
     const size_t o = static_cast<size_t>(ar) * pitch + x0;
-    T hv = T(0);
-    uint32_t hinfo = 0;
+    raw.hv = T(0);
+    raw.hinfo = 0;
     if (active) {
-      unpack(*reinterpret_cast<const V*>(vin + o), r.v);
-      r.info = CPT == 4 ? *reinterpret_cast<const uint32_t*>(info + o)
-                        : static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(info + o));
-      if (has_l) { hv = vin[o - 1]; hinfo = info[o - 1]; }
-      if (has_r) { hv = vin[o + CPT]; hinfo = info[o + CPT]; }
+#pragma unroll
+      for (int k = 0; k < NV; ++k) raw.v[k] = *reinterpret_cast<const V*>(vin + o + k * W);
+      if (CPT == 2) raw.info[0] = *reinterpret_cast<const uint16_t*>(info + o);
+      else {
+#pragma unroll
+        for (int k = 0; k < IW; ++k) raw.info[k] = *reinterpret_cast<const uint32_t*>(info + o + 4 * k);
+      }
+      if (has_l || has_r) { raw.hv = vin[o + hoff]; raw.hinfo = info[o + hoff]; }
     } else {
 #pragma unroll
-      for (int j = 0; j < CPT; ++j) r.v[j] = T(0);
-      r.info = 0;
+      for (int k = 0; k < NV; ++k) raw.v[k] = V();
+#pragma unroll
+      for (int k = 0; k < IW; ++k) raw.info[k] = 0;
     }
-    T rtj = T(0);
+  };
+
+  auto convert = [&](WinRow<T, CPT, TIES>& r) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) unpack(raw.v[k], r.v + k * W);
+#pragma unroll
+    for (int k = 0; k < IW; ++k) r.info[k] = raw.info[k];
+    bool slow = false;
+    T ht = T(0);
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
-      cell_terms<T, TIES>(r.v[j], (r.info >> (8 * j)) & 0xffu, gamma, r.g[j], rtj);
-      if constexpr (TIES) r.rt[j] = rtj;
+      r.g[j] = N::mul(gamma, r.v[j]);
+      if constexpr (TIES)
+        r.rt[j] = round_fast(N::mul(N::add(reward_f(info_of<CPT>(r.info, j), T(0)), r.g[j]), N::scale()), slow);
     }
-    T hg, hrt = T(0);
-    cell_terms<T, TIES>(hv, hinfo, gamma, hg, hrt);
+    const T hg = N::mul(gamma, raw.hv);
+    if constexpr (TIES) ht = round_fast(N::mul(N::add(reward_f(raw.hinfo, T(0)), hg), N::scale()), slow);
+    if constexpr (TIES) {
+      if (slow) {      // rare: re-round everything with rint() (idempotent on integral values)
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          r.rt[j] = N::rnd(N::mul(N::add(reward_f(info_of<CPT>(r.info, j), T(0)), r.g[j]), N::scale()));
+        ht = N::rnd(N::mul(N::add(reward_f(raw.hinfo, T(0)), hg), N::scale()));
+      }
+    }
     r.gl = shfl_up1(r.g[CPT - 1]);
     r.gr = shfl_down1(r.g[0]);
     if (lane == 0) r.gl = hg;
@@ -121,14 +224,18 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     if constexpr (TIES) {
       r.rtl = shfl_up1(r.rt[CPT - 1]);
       r.rtr = shfl_down1(r.rt[0]);
-      if (lane == 0) r.rtl = hrt;
-      if (lane == 31) r.rtr = hrt;
+      if (lane == 0) r.rtl = ht;
+      if (lane == 31) r.rtr = ht;
     }
   };
 
   T dmax = N::neg_inf();
-  load_row(ry0, w[0]);        // array row ry0     = row above the first owned row
-  load_row(ry0 + 1, w[1]);    // array row ry0 + 1 = first owned row
+  const int last_ar = rows + 1;                 // bottom ghost row of the shard's arrays
+  issue_loads(ry0);                             // array row ry0     = row above the first owned row
+  convert(w[0]);
+  issue_loads(ry0 + 1);                         // array row ry0 + 1 = first owned row
+  convert(w[1]);
+  issue_loads(ry0 + 2);
 
   for (int base = ry0; base < ry1; base += 3) {
 #pragma unroll
@@ -138,18 +245,26 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
         WinRow<T, CPT, TIES>& up = w[j % 3];
         WinRow<T, CPT, TIES>& cur = w[(j + 1) % 3];
         WinRow<T, CPT, TIES>& dn = w[(j + 2) % 3];
-        load_row(ry + 2, dn);
+        convert(dn);                               // row ry + 2, loaded during the previous row
+        issue_loads(min(ry + 3, last_ar));         // in flight while this row is computed
         if (active) {
           const size_t o = static_cast<size_t>(ry + 1) * pitch + x0;
           T out[CPT];
-          uint32_t ties = 0;
-          uint32_t pm = 0;
-          if (KIND == GU_POLICY_MASK)
-            pm = CPT == 4 ? *reinterpret_cast<const uint32_t*>(static_cast<const uint8_t*>(policy) + o)
-                          : static_cast<uint32_t>(*reinterpret_cast<const uint16_t*>(static_cast<const uint8_t*>(policy) + o));
+          uint32_t ties[IW];
+          uint32_t pm[IW];
+#pragma unroll
+          for (int k = 0; k < IW; ++k) { ties[k] = 0; pm[k] = 0; }
+          if (KIND == GU_POLICY_MASK) {
+            const uint8_t* pp = static_cast<const uint8_t*>(policy) + o;
+            if (CPT == 2) pm[0] = *reinterpret_cast<const uint16_t*>(pp);
+            else {
+#pragma unroll
+              for (int k = 0; k < IW; ++k) pm[k] = *reinterpret_cast<const uint32_t*>(pp + 4 * k);
+            }
+          }
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            const uint32_t inf = (cur.info >> (8 * c)) & 0xffu;
+            const uint32_t inf = info_of<CPT>(cur.info, c);
             const T gs = cur.g[c];
             // discounted value of the landing cell per action: UP, RIGHT, DOWN, LEFT
             T ga[4];
@@ -158,44 +273,46 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             ga[2] = (inf & 4u) ? gs : dn.g[c];
             ga[3] = (inf & 8u) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
             const T rs = reward_f(inf, T(0));
-            bool tie[4] = {true, true, true, true};
+            const bool live = !(inf & 0x30u);       // terminal rows are all zero (utils.py:70)
+            T ra[4], m = T(0);
             if constexpr (TIES) {
               const T rts = cur.rt[c];
-              T ra[4];
               ra[0] = (inf & 1u) ? rts : up.rt[c];
               ra[1] = (inf & 2u) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
               ra[2] = (inf & 4u) ? rts : dn.rt[c];
               ra[3] = (inf & 8u) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
-              const T m = fmax(fmax(ra[0], ra[1]), fmax(ra[2], ra[3]));
-              const bool live = !(inf & 0x30u);       // terminal rows are all zero (utils.py:70)
-#pragma unroll
-              for (int a = 0; a < 4; ++a) tie[a] = (ra[a] == m) && live;
-              if (WRITE_TIE)
-                ties |= ((tie[0] ? 1u : 0u) | (tie[1] ? 2u : 0u) | (tie[2] ? 4u : 0u) | (tie[3] ? 8u : 0u)) << (8 * c);
+              m = fmax(fmax(ra[0], ra[1]), fmax(ra[2], ra[3]));
             }
-            if (!WRITE_TIE) {
+            if constexpr (WRITE_TIE) {
+              const uint32_t mk = (ra[0] == m ? 1u : 0u) | (ra[1] == m ? 2u : 0u) | (ra[2] == m ? 4u : 0u) |
+                                  (ra[3] == m ? 8u : 0u);
+              ties[c >> 2] |= (live ? mk : 0u) << (8 * (c & 3));
+            } else if constexpr (KIND == GU_POLICY_GREEDY) {
+              out[c] = backup_ties(rs, ra, m, live, ga, inv_cnt);
+            } else if constexpr (KIND == GU_POLICY_PROBS) {
+              const T* pp = static_cast<const T*>(policy) + (o + c) * 4;
               T acc = rs;
-              if (KIND == GU_POLICY_PROBS) {
-                const T* pp = static_cast<const T*>(policy) + (o + c) * 4;
 #pragma unroll
-                for (int a = 0; a < 4; ++a) acc = N::add(acc, N::mul(pp[a], ga[a]));
-              } else {
-                if (KIND == GU_POLICY_MASK) {
+              for (int a = 0; a < 4; ++a) acc = N::add(acc, N::mul(pp[a], ga[a]));
+              out[c] = acc;
+            } else {
+              const uint32_t mk = KIND == GU_POLICY_UNIFORM ? 15u : (pm[c >> 2] >> (8 * (c & 3))) & 15u;
+              const T p = KIND == GU_POLICY_UNIFORM ? T(0.25) : inv_cnt[__popc(mk)];
+              T acc = rs;
 #pragma unroll
-                  for (int a = 0; a < 4; ++a) tie[a] = (pm >> (8 * c + a)) & 1u;
-                }
-                T p = T(0.25);
-                if (KIND != GU_POLICY_UNIFORM)
-                  p = inv_cnt[(tie[0] ? 1 : 0) + (tie[1] ? 1 : 0) + (tie[2] ? 1 : 0) + (tie[3] ? 1 : 0)];
-#pragma unroll
-                for (int a = 0; a < 4; ++a)
-                  if (tie[a]) acc = N::add(acc, N::mul(p, ga[a]));
-              }
+              for (int a = 0; a < 4; ++a)
+                if ((mk >> a) & 1u) acc = N::add(acc, N::mul(p, ga[a]));
               out[c] = acc;
             }
           }
-          if (!WRITE_TIE) {
-            if (x0 + CPT <= g.X) {
+          if constexpr (WRITE_TIE) {
+            if (CPT == 2) *reinterpret_cast<uint16_t*>(tie_out + o) = static_cast<uint16_t>(ties[0]);
+            else {
+#pragma unroll
+              for (int k = 0; k < IW; ++k) *reinterpret_cast<uint32_t*>(tie_out + o + 4 * k) = ties[k];
+            }
+          } else {
+            if (full) {
 #pragma unroll
               for (int c = 0; c < CPT; ++c) dmax = fmax(dmax, N::add(cur.v[c], -out[c]));
             } else {
@@ -203,12 +320,8 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               for (int c = 0; c < CPT; ++c)
                 if (x0 + c < g.X) dmax = fmax(dmax, N::add(cur.v[c], -out[c]));
             }
-          }
-          if (WRITE_TIE) {
-            if (CPT == 4) *reinterpret_cast<uint32_t*>(tie_out + o) = ties;
-            else *reinterpret_cast<uint16_t*>(tie_out + o) = static_cast<uint16_t>(ties);
-          } else {
-            *reinterpret_cast<V*>(vout + o) = pack(out);
+#pragma unroll
+            for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(vout + o + k * W) = pack(out + k * W);
           }
         }
       }
@@ -262,16 +375,27 @@ static inline GridView tview(const gu_grid* g) {
 
 static inline bool tiled_ok(const gu_grid* g, size_t elem, const void* a, const void* b) {
   if (g->info == nullptr) return false;
-  if ((static_cast<size_t>(g->pitch) * elem) % 16 != 0 || g->pitch % 4 != 0) return false;
+  if ((static_cast<size_t>(g->pitch) * elem) % 16 != 0 || g->pitch % 32 != 0) return false;
   if ((reinterpret_cast<uintptr_t>(a) & 15u) || (reinterpret_cast<uintptr_t>(b) & 15u)) return false;
   if (reinterpret_cast<uintptr_t>(g->info) & 3u) return false;
   return true;
 }
 
+#ifndef GU_TILED_NV_F32
+#define GU_TILED_NV_F32 2
+#endif
+#ifndef GU_TILED_NV_F64
+#define GU_TILED_NV_F64 2
+#endif
+template <typename T> struct TiledNV;
+template <> struct TiledNV<float> { static constexpr int value = GU_TILED_NV_F32; };
+template <> struct TiledNV<double> { static constexpr int value = GU_TILED_NV_F64; };
+
 template <typename T, bool WRITE_TIE>
 static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, int kind, const void* policy,
                         T gamma, T* residual, const T* gate, T gate_thr, cudaStream_t st) {
-  constexpr int CPT = Vec<T>::CPT;
+  constexpr int NV = TiledNV<T>::value;
+  constexpr int CPT = Vec<T>::W * NV;
   const int rows = g->row_end - g->row_begin;
   const int cols_per_block = kTiledWarps * 32 * CPT;
   int rpb = 48;                                     // rows per block (halo re-read: 2/48 = 4 %)
@@ -280,7 +404,7 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
   const GridView v = tview(g);
   const uint8_t* info = g->info;
 #define GU_LAUNCH(KIND)                                                                                   \
-  sweep_tiled_kernel<T, KIND, WRITE_TIE><<<grid, kTiledWarps * 32, 0, st>>>(v, info, vin, vout, tie, policy, \
+  sweep_tiled_kernel<T, KIND, WRITE_TIE, NV><<<grid, kTiledWarps * 32, 0, st>>>(v, info, vin, vout, tie, policy, \
                                                                            gamma, residual, gate, gate_thr, rpb)
   if (WRITE_TIE) {
     GU_LAUNCH(GU_POLICY_GREEDY);
