@@ -13,8 +13,8 @@
 // (same operations, same order) the reference computes per (s, a) pair
 // (core/algorithms/utils.py:23-26,65-67); gu_cell.cuh's generic path is the cross-check.
 //
-// Per-cell static data comes from the derived `info` plane (gu_pack_info): bits 0-3 = action a
-// is blocked (grid edge | wall at the target | s terminal), bit 4 goal, bit 5 lava.
+// Per-cell static data comes from the derived `info` plane (gu_pack_info): one bit per action
+// "a is blocked" (grid edge | wall at the target | s terminal) plus the goal and lava bits.
 #include "gu_cell.cuh"
 
 namespace gu {
@@ -31,71 +31,82 @@ __device__ __forceinline__ double2 pack(const double* o) { return make_double2(o
 template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_down1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
 
-__device__ __forceinline__ float reward_f(uint32_t info, float) {
-  return (info & 0x20u) ? -10.0f : ((info & 0x10u) ? 10.0f : -1.0f);
-}
-__device__ __forceinline__ double reward_f(uint32_t info, double) {
-  return (info & 0x20u) ? -10.0 : ((info & 0x10u) ? 10.0 : -1.0);
+// info byte layout (gu_pack_info): bit0 UP blocked, bit1 RIGHT blocked, bit2 DOWN blocked,
+// bit3 goal, bit4 lava, bit5 LEFT blocked.  (info & 0x18) is the byte offset of the cell's entry
+// in the 4-entry {reward, poison} table below (8-byte entries for f32, << 1 for f64).
+constexpr uint32_t kBlkU = 1u, kBlkR = 2u, kBlkD = 4u, kGoal = 8u, kLava = 16u, kBlkL = 32u;
+
+// Per-block lookup tables in shared memory.
+template <typename T>
+struct Luts {
+  T reward[4][2];   // [goal | lava<<1] -> {R (griduniverse_env.py:80-90), poison: 0 or NaN for terminals}
+  T inv_cnt[8];     // 1/len(ties) at index len: exact 1, 1/2, 1/3 (correctly rounded), 1/4
+};
+
+template <typename T>
+__device__ __forceinline__ void init_luts(Luts<T>& l) {
+  const int t = threadIdx.x;
+  if (t < 4) {
+    l.reward[t][0] = (t & 2) ? T(-10) : ((t & 1) ? T(10) : T(-1));
+    l.reward[t][1] = t ? T(CUDART_NAN) : T(0);
+  }
+  if (t < 8) l.inv_cnt[t] = Num<T>::inv(t);
 }
 
-// Bellman backup of one cell for a policy that is uniform on the tie set:
-//   acc = R[s];  for a in 0..3: if tie_a: acc = acc + p * g_a     (utils.py:23-26, left to right)
-// with tie_a = (r_a == m) && live and p = inv_cnt[#ties].  Written in PTX so the four
-// compares feed predicated mul/add pairs directly (no mask round trip through registers).
-__device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], float m, bool live,
-                                             const float (&ga)[4], const float* inv_cnt_smem) {
-  float acc;
-  const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(inv_cnt_smem));
-  asm("{\n\t"
-      ".reg .pred t0, t1, t2, t3, lv;\n\t"
-      ".reg .u32 c, a;\n\t"
-      ".reg .f32 p, x;\n\t"
-      "setp.ne.u32 lv, %11, 0;\n\t"
-      "setp.eq.and.f32 t0, %2, %6, lv;\n\t"
-      "setp.eq.and.f32 t1, %3, %6, lv;\n\t"
-      "setp.eq.and.f32 t2, %4, %6, lv;\n\t"
-      "setp.eq.and.f32 t3, %5, %6, lv;\n\t"
-      "mov.u32 c, 0;\n\t"
-      "@t0 add.u32 c, c, 4;\n\t"
-      "@t1 add.u32 c, c, 4;\n\t"
-      "@t2 add.u32 c, c, 4;\n\t"
-      "@t3 add.u32 c, c, 4;\n\t"
-      "add.u32 a, c, %12;\n\t"
-      "ld.shared.f32 p, [a];\n\t"
-      "mov.f32 %0, %1;\n\t"
-      "mul.rn.f32 x, p, %7;\n\t"
-      "@t0 add.rn.f32 %0, %0, x;\n\t"
-      "mul.rn.f32 x, p, %8;\n\t"
-      "@t1 add.rn.f32 %0, %0, x;\n\t"
-      "mul.rn.f32 x, p, %9;\n\t"
-      "@t2 add.rn.f32 %0, %0, x;\n\t"
-      "mul.rn.f32 x, p, %10;\n\t"
-      "@t3 add.rn.f32 %0, %0, x;\n\t"
-      "}"
-      : "=&f"(acc)
-      : "f"(rs), "f"(ra[0]), "f"(ra[1]), "f"(ra[2]), "f"(ra[3]), "f"(m), "f"(ga[0]), "f"(ga[1]), "f"(ga[2]),
-        "f"(ga[3]), "r"(static_cast<uint32_t>(live)), "r"(lut));
+template <typename T>
+__device__ __forceinline__ T reward_lut(const Luts<T>& l, uint32_t inf) {
+  return *reinterpret_cast<const T*>(reinterpret_cast<const char*>(&l.reward[0][0]) +
+                                     (sizeof(T) == 4 ? (inf & 0x18u) : ((inf & 0x18u) << 1)));
+}
+// {reward, poison} with one 8 / 16-byte shared load
+__device__ __forceinline__ float2 reward_poison_lut(const Luts<float>& l, uint32_t inf) {
+  return *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(&l.reward[0][0]) + (inf & 0x18u));
+}
+__device__ __forceinline__ double2 reward_poison_lut(const Luts<double>& l, uint32_t inf) {
+  return *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(&l.reward[0][0]) + ((inf & 0x18u) << 1));
+}
+
+// Bellman backup of one cell for the policy that is uniform on the tie set (utils.py:23-26,67-71):
+//   acc = R[s];  for a in 0..3 (left to right): if r_a == m: acc = acc + p * g_a,   p = 1/#ties.
+// m carries the terminal "poison" (NaN) so a terminal cell has no ties and keeps acc = R[s].
+//
+// f32: predicate-free.  w_a = (r_a == m) as 1.0f / 0.0f (FSET), the count goes through the
+// mantissa of a magic-number FMA chain into the inv_cnt table, and non-tied actions add
+// (0 * p) * g_a = +-0, which leaves the non-zero running sum bit-identical.
+__device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], float m, const float (&ga)[4],
+                                             const Luts<float>& l) {
+  float w[4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(w[a]) : "f"(ra[a]), "f"(m));
+  float c = 8388608.0f;                                   // 2^23: integers land in the low mantissa bits
+#pragma unroll
+  for (int a = 0; a < 4; ++a) c = __fmaf_rn(w[a], 4.0f, c);
+  const float p = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(&l.inv_cnt[0]) +
+                                                  (__float_as_uint(c) & 0x1cu));
+  float acc = rs;
+#pragma unroll
+  for (int a = 0; a < 4; ++a) acc = __fadd_rn(acc, __fmul_rn(w[a], __fmul_rn(p, ga[a])));
   return acc;
 }
-__device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, bool live,
-                                              const double (&ga)[4], const double* inv_cnt_smem) {
+// f64: compares feed predicated mul / add pairs directly.
+__device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, const double (&ga)[4],
+                                              const Luts<double>& l) {
   double acc;
-  const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(inv_cnt_smem));
+  const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(&l.inv_cnt[0]));
   asm("{\n\t"
-      ".reg .pred t0, t1, t2, t3, lv;\n\t"
+      ".reg .pred t0, t1, t2, t3;\n\t"
       ".reg .u32 c, a;\n\t"
       ".reg .f64 p, x;\n\t"
-      "setp.ne.u32 lv, %11, 0;\n\t"
-      "setp.eq.and.f64 t0, %2, %6, lv;\n\t"
-      "setp.eq.and.f64 t1, %3, %6, lv;\n\t"
-      "setp.eq.and.f64 t2, %4, %6, lv;\n\t"
-      "setp.eq.and.f64 t3, %5, %6, lv;\n\t"
+      "setp.eq.f64 t0, %2, %6;\n\t"
+      "setp.eq.f64 t1, %3, %6;\n\t"
+      "setp.eq.f64 t2, %4, %6;\n\t"
+      "setp.eq.f64 t3, %5, %6;\n\t"
       "mov.u32 c, 0;\n\t"
       "@t0 add.u32 c, c, 8;\n\t"
       "@t1 add.u32 c, c, 8;\n\t"
       "@t2 add.u32 c, c, 8;\n\t"
       "@t3 add.u32 c, c, 8;\n\t"
-      "add.u32 a, c, %12;\n\t"
+      "add.u32 a, c, %11;\n\t"
       "ld.shared.f64 p, [a];\n\t"
       "mov.f64 %0, %1;\n\t"
       "mul.rn.f64 x, p, %7;\n\t"
@@ -109,37 +120,41 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
       "}"
       : "=&d"(acc)
       : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
-        "d"(ga[3]), "r"(static_cast<uint32_t>(live)), "r"(lut));
+        "d"(ga[3]), "r"(lut));
   return acc;
 }
 
 constexpr int kTiledWarps = 4;
 
-// One row of the sliding window: discounted values and rounded scaled q-values of the thread's
-// own columns plus the left / right neighbour columns, the raw V (for the residual), info bytes.
+// One row of the sliding window.  v / info / hv / hinfo are loaded one row of compute ahead
+// ("raw" part); convert() derives the discounted values g and the rounded scaled q-values rt
+// of the thread's own columns plus the left / right neighbour columns.
 template <typename T, int CPT, bool TIES>
 struct WinRow {
+  T v[CPT], hv;
+  uint32_t info[CPT / 4 ? CPT / 4 : 1], hinfo;   // CPT info bytes, little-endian
   T g[CPT], gl, gr;
   T rt[TIES ? CPT : 1], rtl, rtr;
-  T v[CPT];
-  uint32_t info[CPT / 4 ? CPT / 4 : 1];   // CPT info bytes, little-endian
 };
 
-template <int CPT>
 __device__ __forceinline__ uint32_t info_of(const uint32_t* info, int j) {
   return (info[j >> 2] >> (8 * (j & 3))) & 0xffu;
 }
 
 // rint(t) for t = q * 1e8.  f32: |t| >= 2^23 is already integral (the common case: |q| > 0.084).
 // f64: the magic-number add is exact below 2^51.  `need_slow` collects the rare other cases.
-__device__ __forceinline__ float round_fast(float t, bool& need_slow) {
-  need_slow |= fabsf(t) < 8388608.0f;
+__device__ __forceinline__ float round_fast(float t, float& worst) {
+  worst = fminf(worst, fabsf(t));           // slow path if any |t| < 2^23
   return t;
 }
-__device__ __forceinline__ double round_fast(double t, bool& need_slow) {
-  need_slow |= !(fabs(t) < 2251799813685248.0);
+__device__ __forceinline__ double round_fast(double t, double& worst) {
+  worst = fmax(worst, fabs(t));             // slow path if any |t| >= 2^51
   return __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
 }
+__device__ __forceinline__ bool round_needs_slow(float worst) { return worst < 8388608.0f; }
+__device__ __forceinline__ bool round_needs_slow(double worst) { return !(worst < 2251799813685248.0); }
+__device__ __forceinline__ float round_worst_init(float) { return CUDART_INF_F; }
+__device__ __forceinline__ double round_worst_init(double) { return 0.0; }
 
 template <typename T, int KIND, bool WRITE_TIE, int NV>
 __global__ void __launch_bounds__(kTiledWarps * 32)
@@ -153,9 +168,9 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   constexpr int IW = CPT / 4 ? CPT / 4 : 1;   // 32-bit words of info per thread-row
   constexpr bool TIES = (KIND == GU_POLICY_GREEDY) || WRITE_TIE;
   __shared__ T scratch[kTiledWarps];
-  __shared__ T inv_cnt[8];                    // 1/len(ties): exact 1, 1/2, 1/3 (correctly rounded), 1/4
+  __shared__ __align__(16) Luts<T> luts;
   if (gate != nullptr && *gate < gate_thr) return;
-  if (threadIdx.x < 8) inv_cnt[threadIdx.x] = N::inv(threadIdx.x);
+  init_luts(luts);
   __syncthreads();
 
   const int lane = threadIdx.x & 31;
@@ -171,50 +186,45 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const int hoff = has_l ? -1 : CPT;                  // halo column relative to x0
 
   WinRow<T, CPT, TIES> w[3];
-  struct RawRow { V v[NV]; uint32_t info[IW]; T hv; uint32_t hinfo; } raw;
 
-  auto issue_loads = [&](int ar) {
+  auto issue_loads = [&](int ar, WinRow<T, CPT, TIES>& r) {
     const size_t o = static_cast<size_t>(ar) * pitch + x0;
-    raw.hv = T(0);
-    raw.hinfo = 0;
+    r.hv = T(0);
+    r.hinfo = 0;
     if (active) {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) raw.v[k] = *reinterpret_cast<const V*>(vin + o + k * W);
-      if (CPT == 2) raw.info[0] = *reinterpret_cast<const uint16_t*>(info + o);
+      for (int k = 0; k < NV; ++k) unpack(*reinterpret_cast<const V*>(vin + o + k * W), r.v + k * W);
+      if (CPT == 2) r.info[0] = *reinterpret_cast<const uint16_t*>(info + o);
       else {
 #pragma unroll
-        for (int k = 0; k < IW; ++k) raw.info[k] = *reinterpret_cast<const uint32_t*>(info + o + 4 * k);
+        for (int k = 0; k < IW; ++k) r.info[k] = *reinterpret_cast<const uint32_t*>(info + o + 4 * k);
       }
-      if (has_l || has_r) { raw.hv = vin[o + hoff]; raw.hinfo = info[o + hoff]; }
+      if (has_l || has_r) { r.hv = vin[o + hoff]; r.hinfo = info[o + hoff]; }
     } else {
 #pragma unroll
-      for (int k = 0; k < NV; ++k) raw.v[k] = V();
+      for (int j = 0; j < CPT; ++j) r.v[j] = T(0);
 #pragma unroll
-      for (int k = 0; k < IW; ++k) raw.info[k] = 0;
+      for (int k = 0; k < IW; ++k) r.info[k] = 0;
     }
   };
 
   auto convert = [&](WinRow<T, CPT, TIES>& r) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k) unpack(raw.v[k], r.v + k * W);
-#pragma unroll
-    for (int k = 0; k < IW; ++k) r.info[k] = raw.info[k];
-    bool slow = false;
+    T worst = round_worst_init(T(0));
     T ht = T(0);
 #pragma unroll
     for (int j = 0; j < CPT; ++j) {
       r.g[j] = N::mul(gamma, r.v[j]);
       if constexpr (TIES)
-        r.rt[j] = round_fast(N::mul(N::add(reward_f(info_of<CPT>(r.info, j), T(0)), r.g[j]), N::scale()), slow);
+        r.rt[j] = round_fast(N::mul(N::add(reward_lut(luts, info_of(r.info, j)), r.g[j]), N::scale()), worst);
     }
-    const T hg = N::mul(gamma, raw.hv);
-    if constexpr (TIES) ht = round_fast(N::mul(N::add(reward_f(raw.hinfo, T(0)), hg), N::scale()), slow);
+    const T hg = N::mul(gamma, r.hv);
     if constexpr (TIES) {
-      if (slow) {      // rare: re-round everything with rint() (idempotent on integral values)
+      ht = round_fast(N::mul(N::add(reward_lut(luts, r.hinfo), hg), N::scale()), worst);
+      if (round_needs_slow(worst)) {   // rare: re-round everything with rint() (idempotent on integers)
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-          r.rt[j] = N::rnd(N::mul(N::add(reward_f(info_of<CPT>(r.info, j), T(0)), r.g[j]), N::scale()));
-        ht = N::rnd(N::mul(N::add(reward_f(raw.hinfo, T(0)), hg), N::scale()));
+          r.rt[j] = N::rnd(N::mul(N::add(reward_lut(luts, info_of(r.info, j)), r.g[j]), N::scale()));
+        ht = N::rnd(N::mul(N::add(reward_lut(luts, r.hinfo), hg), N::scale()));
       }
     }
     r.gl = shfl_up1(r.g[CPT - 1]);
@@ -231,11 +241,11 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
 
   T dmax = N::neg_inf();
   const int last_ar = rows + 1;                 // bottom ghost row of the shard's arrays
-  issue_loads(ry0);                             // array row ry0     = row above the first owned row
+  issue_loads(ry0, w[0]);                       // array row ry0     = row above the first owned row
+  issue_loads(ry0 + 1, w[1]);                   // array row ry0 + 1 = first owned row
+  issue_loads(ry0 + 2, w[2]);
   convert(w[0]);
-  issue_loads(ry0 + 1);                         // array row ry0 + 1 = first owned row
   convert(w[1]);
-  issue_loads(ry0 + 2);
 
   for (int base = ry0; base < ry1; base += 3) {
 #pragma unroll
@@ -246,7 +256,9 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
         WinRow<T, CPT, TIES>& cur = w[(j + 1) % 3];
         WinRow<T, CPT, TIES>& dn = w[(j + 2) % 3];
         convert(dn);                               // row ry + 2, loaded during the previous row
-        issue_loads(min(ry + 3, last_ar));         // in flight while this row is computed
+        // the row after that goes into the raw fields of `up` (its v / info are dead, its g / rt
+        // stay valid for this row's compute); the loads are in flight while this row is computed
+        issue_loads(min(ry + 3, last_ar), up);
         if (active) {
           const size_t o = static_cast<size_t>(ry + 1) * pitch + x0;
           T out[CPT];
@@ -264,31 +276,32 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
           }
 #pragma unroll
           for (int c = 0; c < CPT; ++c) {
-            const uint32_t inf = info_of<CPT>(cur.info, c);
+            const uint32_t inf = info_of(cur.info, c);
             const T gs = cur.g[c];
             // discounted value of the landing cell per action: UP, RIGHT, DOWN, LEFT
             T ga[4];
-            ga[0] = (inf & 1u) ? gs : up.g[c];
-            ga[1] = (inf & 2u) ? gs : (c == CPT - 1 ? cur.gr : cur.g[c + 1 < CPT ? c + 1 : c]);
-            ga[2] = (inf & 4u) ? gs : dn.g[c];
-            ga[3] = (inf & 8u) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
-            const T rs = reward_f(inf, T(0));
-            const bool live = !(inf & 0x30u);       // terminal rows are all zero (utils.py:70)
+            ga[0] = (inf & kBlkU) ? gs : up.g[c];
+            ga[1] = (inf & kBlkR) ? gs : (c == CPT - 1 ? cur.gr : cur.g[c + 1 < CPT ? c + 1 : c]);
+            ga[2] = (inf & kBlkD) ? gs : dn.g[c];
+            ga[3] = (inf & kBlkL) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
+            const auto rp = reward_poison_lut(luts, inf);   // {R[s], NaN if s terminal else 0}
+            const T rs = rp.x;
             T ra[4], m = T(0);
             if constexpr (TIES) {
               const T rts = cur.rt[c];
-              ra[0] = (inf & 1u) ? rts : up.rt[c];
-              ra[1] = (inf & 2u) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
-              ra[2] = (inf & 4u) ? rts : dn.rt[c];
-              ra[3] = (inf & 8u) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
-              m = fmax(fmax(ra[0], ra[1]), fmax(ra[2], ra[3]));
+              ra[0] = (inf & kBlkU) ? rts : up.rt[c];
+              ra[1] = (inf & kBlkR) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
+              ra[2] = (inf & kBlkD) ? rts : dn.rt[c];
+              ra[3] = (inf & kBlkL) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
+              // terminal rows are all zero (utils.py:70): NaN never compares equal
+              m = N::add(fmax(fmax(ra[0], ra[1]), fmax(ra[2], ra[3])), rp.y);
             }
             if constexpr (WRITE_TIE) {
               const uint32_t mk = (ra[0] == m ? 1u : 0u) | (ra[1] == m ? 2u : 0u) | (ra[2] == m ? 4u : 0u) |
                                   (ra[3] == m ? 8u : 0u);
-              ties[c >> 2] |= (live ? mk : 0u) << (8 * (c & 3));
+              ties[c >> 2] |= mk << (8 * (c & 3));
             } else if constexpr (KIND == GU_POLICY_GREEDY) {
-              out[c] = backup_ties(rs, ra, m, live, ga, inv_cnt);
+              out[c] = backup_ties(rs, ra, m, ga, luts);
             } else if constexpr (KIND == GU_POLICY_PROBS) {
               const T* pp = static_cast<const T*>(policy) + (o + c) * 4;
               T acc = rs;
@@ -297,7 +310,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               out[c] = acc;
             } else {
               const uint32_t mk = KIND == GU_POLICY_UNIFORM ? 15u : (pm[c >> 2] >> (8 * (c & 3))) & 15u;
-              const T p = KIND == GU_POLICY_UNIFORM ? T(0.25) : inv_cnt[__popc(mk)];
+              const T p = KIND == GU_POLICY_UNIFORM ? T(0.25) : luts.inv_cnt[__popc(mk)];
               T acc = rs;
 #pragma unroll
               for (int a = 0; a < 4; ++a)
@@ -356,11 +369,11 @@ pack_info_kernel(GridView g, uint8_t* __restrict__ info) {
     const uint32_t goal = bit(g.goal, 0, x), lava = bit(g.lava, 0, x);
     const bool term = goal | lava;
     const bool inner_up = ar > 0, inner_dn = ar < (g.row_end - g.row_begin + 1);   // neighbour row is in the arrays
-    const uint32_t bu = (term || y == 0 || (inner_up && bit(g.wall, -1, x))) ? 1u : 0u;
-    const uint32_t br = (term || x == g.X - 1 || bit(g.wall, 0, x + 1)) ? 2u : 0u;
-    const uint32_t bd = (term || y == g.Y - 1 || (inner_dn && bit(g.wall, 1, x))) ? 4u : 0u;
-    const uint32_t bl = (term || x == 0 || bit(g.wall, 0, x - 1)) ? 8u : 0u;
-    v = bu | br | bd | bl | (goal << 4) | (lava << 5);
+    const uint32_t bu = (term || y == 0 || (inner_up && bit(g.wall, -1, x))) ? kBlkU : 0u;
+    const uint32_t br = (term || x == g.X - 1 || bit(g.wall, 0, x + 1)) ? kBlkR : 0u;
+    const uint32_t bd = (term || y == g.Y - 1 || (inner_dn && bit(g.wall, 1, x))) ? kBlkD : 0u;
+    const uint32_t bl = (term || x == 0 || bit(g.wall, 0, x - 1)) ? kBlkL : 0u;
+    v = bu | br | bd | bl | (goal ? kGoal : 0u) | (lava ? kLava : 0u);
   }
   info[static_cast<size_t>(ar) * g.pitch + x] = static_cast<uint8_t>(v);
 }

@@ -145,8 +145,8 @@ int gu_look_step_ahead(const gu_levels* lv, int64_t m, const int32_t* states, co
  * row, bit (x & 31) of word (x >> 5); bits at x >= X are zero.
  * pitch >= X.
  * `info` (optional, may be NULL): derived per-cell byte plane built once per level by
- * gu_pack_info, same padded layout as the per-cell arrays: bits 0-3 = action a is blocked
- * (grid edge | wall at the target | cell terminal), bit 4 goal, bit 5 lava.  With it, and
+ * gu_pack_info, same padded layout as the per-cell arrays: bit0/1/2/5 = UP/RIGHT/DOWN/LEFT is
+ * blocked (grid edge | wall at the target | cell terminal), bit 3 goal, bit 4 lava.  With it, and
  * with pitch % 4 == 0, pitch*sizeof(T) % 16 == 0 and 16-byte aligned arrays, the sweep /
  * greedy entry points run the register-tiled kernels; otherwise the layout-agnostic ones. */
 typedef struct {
