@@ -46,7 +46,8 @@ _LIB = None
 
 
 def library_path():
-    return _build.LIB_PATH
+    # GU_B200_LIB selects a tuning variant built by build.build_variant (developer use only)
+    return os.environ.get("GU_B200_LIB", _build.LIB_PATH)
 
 
 def lib():

@@ -50,6 +50,14 @@ def _digest():
     return h.hexdigest()
 
 
+def build_variant(out_path, defines):
+    """Developer helper: build a tuning variant (extra -D flags) to another path."""
+    cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f not in ("-Xptxas", "-v")] + ["-D" + d for d in defines] + \
+        ["-I", INCLUDE, "-I", CSRC, "-o", out_path] + _sources()
+    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    return out_path
+
+
 def build_library(force=False, verbose=False):
     """Compile every .cu under csrc/ into one shared library.  Returns the library path."""
     os.makedirs(LIB_DIR, exist_ok=True)

@@ -124,7 +124,13 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
   return acc;
 }
 
-constexpr int kTiledWarps = 4;
+#ifndef GU_TILED_WARPS
+#define GU_TILED_WARPS 4
+#endif
+#ifndef GU_TILED_PREFETCH_ROWS
+#define GU_TILED_PREFETCH_ROWS 3
+#endif
+constexpr int kTiledWarps = GU_TILED_WARPS;
 
 // One row of the sliding window.  v / info / hv / hinfo are loaded one row of compute ahead
 // ("raw" part); convert() derives the discounted values g and the rounded scaled q-values rt
@@ -187,8 +193,24 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
 
   WinRow<T, CPT, TIES> w[3];
 
+  // L2 prefetch of the warp's strip kPrefetchRows rows ahead of the demand loads: one 128-byte
+  // line per lane (V lines first, then the info lines), so the demand loads hit L2.
+  constexpr int kPrefetchRows = GU_TILED_PREFETCH_ROWS;
+  constexpr int kVLines = 32 * CPT * static_cast<int>(sizeof(T)) / 128;
+  constexpr int kILines = (32 * CPT + 127) / 128;
+  const int wx0 = x0 - lane * CPT;                    // first column of the warp's strip
+  const char* pf_base = nullptr;
+  if (lane < kVLines) pf_base = reinterpret_cast<const char*>(vin + wx0) + lane * 128;
+  else if (lane < kVLines + kILines) pf_base = reinterpret_cast<const char*>(info + wx0) + (lane - kVLines) * 128;
+  const size_t pf_pitch = lane < kVLines ? pitch * sizeof(T) : pitch;
+  const bool pf_on = pf_base != nullptr && wx0 + (lane < kVLines ? lane * (128 / static_cast<int>(sizeof(T))) : (lane - kVLines) * 128) < g.pitch;
+
   auto issue_loads = [&](int ar, WinRow<T, CPT, TIES>& r) {
     const size_t o = static_cast<size_t>(ar) * pitch + x0;
+    if (pf_on) {
+      const int par = min(ar + kPrefetchRows, rows + 1);
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + static_cast<size_t>(par) * pf_pitch));
+    }
     r.hv = T(0);
     r.hinfo = 0;
     if (active) {
@@ -397,6 +419,9 @@ static inline bool tiled_ok(const gu_grid* g, size_t elem, const void* a, const 
 #ifndef GU_TILED_NV_F32
 #define GU_TILED_NV_F32 2
 #endif
+#ifndef GU_TILED_ROWS_PER_BLOCK
+#define GU_TILED_ROWS_PER_BLOCK 48
+#endif
 #ifndef GU_TILED_NV_F64
 #define GU_TILED_NV_F64 2
 #endif
@@ -411,7 +436,7 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
   constexpr int CPT = Vec<T>::W * NV;
   const int rows = g->row_end - g->row_begin;
   const int cols_per_block = kTiledWarps * 32 * CPT;
-  int rpb = 48;                                     // rows per block (halo re-read: 2/48 = 4 %)
+  int rpb = GU_TILED_ROWS_PER_BLOCK;               // rows per block (halo re-read: 2 rows per block)
   dim3 grid((g->X + cols_per_block - 1) / cols_per_block, (rows + rpb - 1) / rpb);
   if (grid.y > 65535u) return GU_ERR_SHAPE;
   const GridView v = tview(g);

@@ -1,0 +1,28 @@
+"""Build tuning variants of libgu_b200.so locally, then (on the GPU box) time each one."""
+import itertools, os, subprocess, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+VDIR = os.path.join(ROOT, "griduniverse_b200", "lib", "variants")
+GRID = {"GU_TILED_MIN_BLOCKS": [1, 5, 6], "GU_TILED_PREFETCH_ROWS": [2, 3, 4], "GU_TILED_ROWS_PER_BLOCK": [24, 48]}
+def variants():
+    keys = sorted(GRID)
+    for vals in itertools.product(*[GRID[k] for k in keys]):
+        yield ["%s=%d" % (k, v) for k, v in zip(keys, vals)]
+if sys.argv[1] == "build":
+    from griduniverse_b200 import build
+    os.makedirs(VDIR, exist_ok=True)
+    from concurrent.futures import ThreadPoolExecutor
+    def one(d):
+        name = "_".join(x.split("=")[1] for x in d)
+        return build.build_variant(os.path.join(VDIR, "libgu_%s.so" % name), d)
+    with ThreadPoolExecutor(8) as ex:
+        for p in ex.map(one, list(variants())):
+            print("built", p)
+else:
+    for d in variants():
+        name = "_".join(x.split("=")[1] for x in d)
+        env = dict(os.environ, GU_B200_LIB=os.path.join(VDIR, "libgu_%s.so" % name), ONLY="f32")
+        out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_perf.py"), "sweep"], env=env,
+                             capture_output=True, text=True).stdout
+        print(" ".join(d))
+        print("\n".join(l for l in out.splitlines() if "greedy " in l or "uniform" in l))
