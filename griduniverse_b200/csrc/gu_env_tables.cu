@@ -1,20 +1,360 @@
-// gu_env_tables.cu -- table-driven rollout fast paths (transition tables staged in shared
-// memory).  Filled in after the layout-agnostic kernels are parity-green; until then no
-// shape has a table format and gu_rollout uses rollout_generic_kernel.
-#include "gu_common.cuh"
+// gu_env_tables.cu -- table-driven rollout kernels (transition tables staged in shared memory).
+//
+// A level is static, so look_step_ahead (core/envs/griduniverse_env.py:136-155) can be
+// tabulated once per level: for every (cell, action) the landing cell plus the goal / lava
+// flags of the landing cell (which give reward and done, :155,163-174).  gu_pack_tables builds
+// the tables on the device with the same transition() code the layout-agnostic kernels use;
+// the rollout kernels copy each env's table into shared memory once per launch and then pay
+// one conflict-free shared load per env step.
+//
+// Formats
+//   NT8  (per-env levels, X*Y <= 64):  one 32-bit word per cell, byte a = landing cell of
+//        action a in bits 0-5, goal flag bit 6, lava flag bit 7 (goal cleared when lava is set:
+//        lava wins, griduniverse_env.py:86-90).  WORD-MAJOR uint32[cells][N].
+//   NT16 (shared level, X*Y <= 16383): uint16 per (cell, action): landing in bits 0-13, goal
+//        bit 14, lava bit 15.  uint16[cells][4], read by every env of the batch.
+#include "gu_env.cuh"
 
 namespace gu {
 
-int rollout_tables(const gu_levels*, int64_t, int64_t, const int32_t*, int32_t*, int32_t*, int32_t*,
-                   uint8_t*, const int32_t*, int32_t*, int32_t*, int64_t*, const uint32_t*, uint32_t,
-                   cudaStream_t) {
+enum TableFormat { kTableNone = 0, kTableNT8 = 1, kTableNT16 = 2 };
+
+static TableFormat table_format(const gu_levels* lv) {
+  const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
+  if (lv->per_env && cells <= 64) return kTableNT8;
+  if (!lv->per_env && cells <= 16383) return kTableNT16;
+  return kTableNone;
+}
+
+// ---- table construction -------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+pack_nt8_kernel(LevelsView lv, uint32_t* __restrict__ tables) {
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (env >= lv.N) return;
+  const int cells = lv.X * lv.Y;
+  for (int s = 0; s < cells; ++s) {
+    uint32_t word = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      int n, r;
+      bool term;
+      transition(lv, env, s, a, true, n, r, term);
+      const uint32_t f = r == kRewardLava ? 0x80u : (r == kRewardGoal ? 0x40u : 0u);
+      word |= (static_cast<uint32_t>(n) | f) << (8 * a);
+    }
+    tables[static_cast<int64_t>(s) * lv.N + env] = word;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (cell, action)
+  const int cells = lv.X * lv.Y;
+  if (i >= cells * 4) return;
+  int n, r;
+  bool term;
+  transition(lv, 0, i >> 2, i & 3, true, n, r, term);
+  const uint32_t f = r == kRewardLava ? 0x8000u : (r == kRewardGoal ? 0x4000u : 0u);
+  tables[i] = static_cast<uint16_t>(static_cast<uint32_t>(n) | f);
+}
+
+// ---- rollout over NT8 tables --------------------------------------------------------------
+// EPT consecutive envs per thread (EPT = 4: actions / outputs move as int4 / uchar4 requests).
+// Shared-memory layout: word of (cell s, env slot k of thread tid) at s*EPB + k*THREADS + tid,
+// EPB = THREADS*EPT, so every shared load of a warp hits 32 different banks.
+// Only a thread's own slots are ever read by it: no barrier is needed after staging.
+constexpr int kNt8Threads = 128;
+constexpr int kNt8Unroll = 8;    // action rows kept in flight per thread (software prefetch)
+
+template <int EPT> struct ActVec;
+template <> struct ActVec<4> { using type = int4; };
+template <> struct ActVec<1> { using type = int; };
+
+__device__ __forceinline__ void unpack_act(const int4& v, int (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
+__device__ __forceinline__ void unpack_act(const int& v, int (&a)[1]) { a[0] = v; }
+
+template <int EPT, bool TRAJ>
+__global__ void __launch_bounds__(kNt8Threads)
+rollout_nt8_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restrict__ tables,
+                   const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+                   int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                   const int32_t* __restrict__ start, const int32_t* __restrict__ start_choice,
+                   int32_t* __restrict__ env_return, int32_t* __restrict__ env_done, int64_t* stats,
+                   uint32_t flags) {
+  extern __shared__ uint32_t tab[];
+  using AV = typename ActVec<EPT>::type;
+  constexpr int EPB = kNt8Threads * EPT;
+  const int tid = threadIdx.x;
+  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kNt8Threads + tid) * EPT;
+  const bool live = env0 < N;                 // N % EPT == 0 is guaranteed by the launcher
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
+  long long rsum = 0, dcnt = 0;
+
+  if (live) {
+    // stage this thread's tables: coalesced 16-byte loads of EPT consecutive envs per cell
+    for (int s = 0; s < cells; ++s) {
+      int wv[EPT];
+      unpack_act(*reinterpret_cast<const AV*>(tables + static_cast<int64_t>(s) * N + env0), wv);
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) tab[s * EPB + k * kNt8Threads + tid] = static_cast<uint32_t>(wv[k]);
+    }
+    int p[EPT], st[EPT];
+    unpack_act(*reinterpret_cast<const AV*>(pos + env0), p);
+    unpack_act(*reinterpret_cast<const AV*>(start + env0), st);
+    uint32_t word[EPT], fsum[EPT], fsq[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      word[k] = tab[p[k] * EPB + k * kNt8Threads + tid];
+      fsum[k] = 0;
+      fsq[k] = 0;
+    }
+    const int32_t* ap = actions + env0;
+    AV abuf[kNt8Unroll];
+#pragma unroll
+    for (int u = 0; u < kNt8Unroll; ++u)
+      if (u < T) abuf[u] = *reinterpret_cast<const AV*>(ap + static_cast<int64_t>(u) * N);
+    for (int64_t t0 = 0; t0 < T; t0 += kNt8Unroll) {
+      AV acur[kNt8Unroll];
+#pragma unroll
+      for (int u = 0; u < kNt8Unroll; ++u) acur[u] = abuf[u];
+      // next batch of action rows goes in flight before this batch is consumed
+#pragma unroll
+      for (int u = 0; u < kNt8Unroll; ++u)
+        if (t0 + kNt8Unroll + u < T)
+          abuf[u] = *reinterpret_cast<const AV*>(ap + (t0 + kNt8Unroll + u) * N);
+#pragma unroll
+      for (int u = 0; u < kNt8Unroll; ++u) {
+        const int64_t t = t0 + u;
+        if (t < T) {
+          int a[EPT];
+          unpack_act(acur[u], a);
+          int ob[EPT], rw[EPT];
+          uint32_t dn[EPT];
+          int sc[EPT];
+          if (start_choice != nullptr) unpack_act(*reinterpret_cast<const AV*>(start_choice + t * N + env0), sc);
+#pragma unroll
+          for (int k = 0; k < EPT; ++k) {
+            // byte (a & 3) of the cell's word: the funnel shift takes its amount modulo 32
+            const uint32_t v = __funnelshift_r(word[k], 0u, static_cast<uint32_t>(a[k]) << 3);
+            const uint32_t f = v & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
+            int n = static_cast<int>(v & 0x3fu);
+            if (TRAJ) {
+              ob[k] = n;
+              rw[k] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
+              dn[k] = f ? 1u : 0u;
+            }
+            fsum[k] += f;                               // 64*goals + 128*lavas
+            fsq[k] += f * f;                            // 4096*goals + 16384*lavas
+            if (auto_reset && f) n = start_choice != nullptr ? sc[k] : st[k];
+            p[k] = n;
+            word[k] = tab[n * EPB + k * kNt8Threads + tid];
+          }
+          if (TRAJ) {
+            const int64_t o = t * N + env0;
+            if (EPT == 4) {
+              if (obs) *reinterpret_cast<int4*>(obs + o) = make_int4(ob[0], ob[1 % EPT], ob[2 % EPT], ob[3 % EPT]);
+              if (reward) *reinterpret_cast<int4*>(reward + o) = make_int4(rw[0], rw[1 % EPT], rw[2 % EPT], rw[3 % EPT]);
+              if (done) *reinterpret_cast<uchar4*>(done + o) = make_uchar4(dn[0], dn[1 % EPT], dn[2 % EPT], dn[3 % EPT]);
+            } else {
+              if (obs) obs[o] = ob[0];
+              if (reward) reward[o] = rw[0];
+              if (done) done[o] = static_cast<uint8_t>(dn[0]);
+            }
+          }
+        }
+      }
+    }
+    int er[EPT], ed[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
+      const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
+      const long long dones = static_cast<long long>(goals) + lavas;
+      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
+      rsum += ret;
+      dcnt += dones;
+      er[k] = static_cast<int>(ret);
+      ed[k] = static_cast<int>(dones);
+    }
+    if (EPT == 4) {
+      *reinterpret_cast<int4*>(pos + env0) = make_int4(p[0], p[1 % EPT], p[2 % EPT], p[3 % EPT]);
+      if (env_return) {
+        int4* q = reinterpret_cast<int4*>(env_return + env0);
+        int4 old = accumulate ? *q : make_int4(0, 0, 0, 0);
+        *q = make_int4(old.x + er[0], old.y + er[1 % EPT], old.z + er[2 % EPT], old.w + er[3 % EPT]);
+      }
+      if (env_done) {
+        int4* q = reinterpret_cast<int4*>(env_done + env0);
+        int4 old = accumulate ? *q : make_int4(0, 0, 0, 0);
+        *q = make_int4(old.x + ed[0], old.y + ed[1 % EPT], old.z + ed[2 % EPT], old.w + ed[3 % EPT]);
+      }
+    } else {
+      pos[env0] = p[0];
+      if (env_return) env_return[env0] = er[0] + (accumulate ? env_return[env0] : 0);
+      if (env_done) env_done[env0] = ed[0] + (accumulate ? env_done[env0] : 0);
+    }
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
+// ---- rollout over a shared NT16 table -------------------------------------------------------
+constexpr int kNt16Threads = 256;
+
+template <bool TRAJ>
+__global__ void __launch_bounds__(kNt16Threads)
+rollout_nt16_kernel(int64_t N, int64_t T, int cells, const uint16_t* __restrict__ tables,
+                    const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+                    int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                    const int32_t* __restrict__ start, const int32_t* __restrict__ start_choice,
+                    int32_t* __restrict__ env_return, int32_t* __restrict__ env_done, int64_t* stats,
+                    uint32_t flags) {
+  extern __shared__ uint32_t tab32[];
+  uint16_t* tab = reinterpret_cast<uint16_t*>(tab32);
+  for (int i = threadIdx.x; i < cells * 2; i += kNt16Threads)
+    tab32[i] = reinterpret_cast<const uint32_t*>(tables)[i];
+  __syncthreads();
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * kNt16Threads + threadIdx.x;
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
+  long long rsum = 0, dcnt = 0;
+  if (env < N) {
+    int p = pos[env];
+    const int st = __ldg(start);
+    constexpr int U = 8;
+    int abuf[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      if (u < T) abuf[u] = __ldg(actions + static_cast<int64_t>(u) * N + env);
+    for (int64_t t0 = 0; t0 < T; t0 += U) {
+      int acur[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) acur[u] = abuf[u];
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (t0 + U + u < T) abuf[u] = __ldg(actions + (t0 + U + u) * N + env);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int64_t t = t0 + u;
+        if (t < T) {
+          const uint32_t v = tab[p * 4 + (acur[u] & 3)];
+          const int n = static_cast<int>(v & 0x3fffu);
+          const bool lava = v & 0x8000u, goal = v & 0x4000u;
+          const int r = lava ? kRewardLava : (goal ? kRewardGoal : kRewardStep);
+          const bool d = lava | goal;
+          if (TRAJ) {
+            const int64_t o = t * N + env;
+            if (obs) obs[o] = n;
+            if (reward) reward[o] = r;
+            if (done) done[o] = d;
+          }
+          rsum += r;
+          dcnt += d ? 1 : 0;
+          p = n;
+          if (auto_reset && d) p = start_choice != nullptr ? __ldg(start_choice + t * N + env) : st;
+        }
+      }
+    }
+    pos[env] = p;
+    if (env_return) env_return[env] = static_cast<int>(rsum) + (accumulate ? env_return[env] : 0);
+    if (env_done) env_done[env] = static_cast<int>(dcnt) + (accumulate ? env_done[env] : 0);
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
+static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+static inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
+
+int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
+                   int32_t* reward, uint8_t* done, const int32_t* start_choice, int32_t* env_return,
+                   int32_t* env_done, int64_t* stats, const uint32_t* tables, uint32_t flags, cudaStream_t st) {
+  if (flags & GU_FLAG_NO_CARE_TERMINAL) return GU_ERR_UNSUPPORTED;   // tables tabulate care_about_terminal=True
+  if (T >= (1 << 18)) return GU_ERR_UNSUPPORTED;                     // packed goal / lava counters are 32-bit
+  const TableFormat fmt = table_format(lv);
+  const int cells = lv->X * lv->Y;
+  const bool traj = obs || reward || done;
+  if (fmt == kTableNT8) {
+    const bool vec = (n % 4 == 0) && al16(actions) && al16(pos) && al16(tables) && al16(lv->start) &&
+                     (!obs || al16(obs)) && (!reward || al16(reward)) && (!done || al4(done)) &&
+                     (!start_choice || al16(start_choice)) && (!env_return || al16(env_return)) &&
+                     (!env_done || al16(env_done));
+    const int ept = vec ? 4 : 1;
+    const size_t smem = static_cast<size_t>(cells) * 4 * kNt8Threads * ept;
+    const int64_t threads = n / ept;
+    const unsigned blocks = static_cast<unsigned>((threads + kNt8Threads - 1) / kNt8Threads);
+#define GU_NT8(EPT, TRAJ)                                                                                     \
+  do {                                                                                                        \
+    cudaError_t e = cudaFuncSetAttribute(rollout_nt8_kernel<EPT, TRAJ>,                                       \
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
+    if (e != cudaSuccess) return static_cast<int>(e);                                                         \
+    rollout_nt8_kernel<EPT, TRAJ><<<blocks, kNt8Threads, smem, st>>>(n, T, cells, tables, actions, pos, obs,  \
+                                                                     reward, done, lv->start, start_choice,   \
+                                                                     env_return, env_done, stats, flags);     \
+  } while (0)
+    if (vec && traj) GU_NT8(4, true);
+    else if (vec) GU_NT8(4, false);
+    else if (traj) GU_NT8(1, true);
+    else GU_NT8(1, false);
+#undef GU_NT8
+    GU_CHECK_LAUNCH();
+    return GU_OK;
+  }
+  if (fmt == kTableNT16) {
+    const size_t smem = static_cast<size_t>(cells) * 8;
+    const unsigned blocks = static_cast<unsigned>((n + kNt16Threads - 1) / kNt16Threads);
+    const uint16_t* t16 = reinterpret_cast<const uint16_t*>(tables);
+    if (traj) {
+      cudaError_t e = cudaFuncSetAttribute(rollout_nt16_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      rollout_nt16_kernel<true><<<blocks, kNt16Threads, smem, st>>>(n, T, cells, t16, actions, pos, obs, reward, done,
+                                                                   lv->start, start_choice, env_return, env_done,
+                                                                   stats, flags);
+    } else {
+      cudaError_t e = cudaFuncSetAttribute(rollout_nt16_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      rollout_nt16_kernel<false><<<blocks, kNt16Threads, smem, st>>>(n, T, cells, t16, actions, pos, obs, reward, done,
+                                                                    lv->start, start_choice, env_return, env_done,
+                                                                    stats, flags);
+    }
+    GU_CHECK_LAUNCH();
+    return GU_OK;
+  }
   return GU_ERR_UNSUPPORTED;
 }
 
 }  // namespace gu
 
-extern "C" __attribute__((visibility("default"))) int64_t gu_tables_bytes(const gu_levels*, int64_t) { return 0; }
+using namespace gu;
 
-extern "C" __attribute__((visibility("default"))) int gu_pack_tables(const gu_levels*, int64_t, uint32_t*, uint32_t, void*) {
-  return GU_ERR_UNSUPPORTED;
+extern "C" __attribute__((visibility("default"))) int64_t gu_tables_bytes(const gu_levels* lv, int64_t n) {
+  if (!lv || n < 0) return 0;
+  const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
+  switch (table_format(lv)) {
+    case kTableNT8: return cells * 4 * n;
+    case kTableNT16: return cells * 8;
+    default: return 0;
+  }
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_pack_tables(const gu_levels* lv, int64_t n, uint32_t* tables,
+                                                                     uint32_t flags, void* stream) {
+  int rc = check_levels(lv, n);
+  if (rc) return rc;
+  if (!tables) return GU_ERR_NULL;
+  (void)flags;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const TableFormat fmt = table_format(lv);
+  if (fmt == kTableNT8) {
+    if (n == 0) return GU_OK;
+    pack_nt8_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(view_of(lv, n), tables);
+  } else if (fmt == kTableNT16) {
+    const int cells = lv->X * lv->Y;
+    pack_nt16_kernel<<<(cells * 4 + 127) / 128, 128, 0, st>>>(view_of(lv, 1), reinterpret_cast<uint16_t*>(tables));
+  } else {
+    return GU_ERR_UNSUPPORTED;
+  }
+  GU_CHECK_LAUNCH();
+  return GU_OK;
 }
