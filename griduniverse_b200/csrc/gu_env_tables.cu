@@ -198,6 +198,148 @@ rollout_nt8_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restrict__
   publish_stats(rsum, dcnt, stats);
 }
 
+// ---- rollout over NT8 tables, TMA bulk-copy staged (the fast path) ----------------------------
+// One warp owns 128 consecutive envs; lane l steps envs l, l+32, l+64, l+96 of the warp's range, so a
+// warp's words of one table row / one action row are 512 contiguous bytes in HBM and, copied
+// verbatim into shared memory, are read back conflict-free (bank = lane).  All HBM traffic is
+// issued by one elected lane as cp.async.bulk (TMA, SASS UBLKCP) copies that complete on
+// per-warp mbarriers: the 32 KB transition table once, then the action stream in batches of
+// kBulkRows time steps through a kBulkStages-deep ring, so kBulkStages*8 KB per warp are in
+// flight while the other lanes step.  No block-level barrier: warps are independent.
+constexpr int kBulkWarps = 4;
+constexpr int kBulkRows = 16;      // action rows (time steps) per batch
+constexpr int kBulkStages = 2;
+constexpr int kBulkEnvsPerWarp = 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "GU_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra GU_DONE;\n\t"
+      "bra GU_WAIT;\n\t"
+      "GU_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+template <bool TRAJ>
+__global__ void __launch_bounds__(kBulkWarps * 32)
+rollout_nt8_bulk_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restrict__ tables,
+                        const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+                        int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                        const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
+                        int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int EPW = kBulkEnvsPerWarp, ROWB = EPW * 4;              // 512 bytes per row per warp
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t per_warp = static_cast<size_t>(cells) * ROWB + kBulkStages * kBulkRows * ROWB;
+  uint8_t* wbase = smem_raw + warp * per_warp;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(wbase);                                   // [cells][128]
+  uint32_t* act = reinterpret_cast<uint32_t*>(wbase + static_cast<size_t>(cells) * ROWB);  // [stages][rows][128]
+  __shared__ __align__(8) uint64_t bars[kBulkWarps][kBulkStages + 1];
+  const uint32_t bar_tab = smem_u32(&bars[warp][kBulkStages]);
+  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBulkWarps + warp) * EPW;   // N % 128 == 0
+  const bool live = env0 < N;
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
+  const int64_t nbatch = (T + kBulkRows - 1) / kBulkRows;
+  long long rsum = 0, dcnt = 0;
+
+  if (live) {
+    if (lane == 0) {
+      for (int i = 0; i <= kBulkStages; ++i) mbar_init(smem_u32(&bars[warp][i]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue_batch = [&](int64_t b) {          // lane 0 only
+      const int stage = static_cast<int>(b % kBulkStages);
+      const int64_t t0 = b * kBulkRows;
+      const int rows = static_cast<int>(T - t0 < kBulkRows ? T - t0 : kBulkRows);
+      const uint32_t bar = smem_u32(&bars[warp][stage]);
+      mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROWB);
+      for (int r = 0; r < rows; ++r)
+        bulk_g2s(smem_u32(act + (stage * kBulkRows + r) * EPW), actions + (t0 + r) * N + env0, ROWB, bar);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(bar_tab, static_cast<uint32_t>(cells) * ROWB);
+      for (int s = 0; s < cells; ++s)
+        bulk_g2s(smem_u32(tab + s * EPW), tables + static_cast<int64_t>(s) * N + env0, ROWB, bar_tab);
+      for (int64_t b = 0; b < kBulkStages && b < nbatch; ++b) issue_batch(b);
+    }
+    int p[4], st[4];
+    uint32_t word[4], fsum[4], fsq[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      p[k] = pos[env0 + k * 32 + lane];
+      st[k] = start[env0 + k * 32 + lane];
+      fsum[k] = 0;
+      fsq[k] = 0;
+    }
+    mbar_wait(bar_tab, 0);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) word[k] = tab[p[k] * EPW + k * 32 + lane];
+
+    for (int64_t b = 0; b < nbatch; ++b) {
+      const int stage = static_cast<int>(b % kBulkStages);
+      const int64_t t0 = b * kBulkRows;
+      const int rows = static_cast<int>(T - t0 < kBulkRows ? T - t0 : kBulkRows);
+      mbar_wait(smem_u32(&bars[warp][stage]), static_cast<uint32_t>((b / kBulkStages) & 1));
+      const uint32_t* arow = act + stage * kBulkRows * EPW + lane;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t a = arow[r * EPW + k * 32];
+          // byte (a & 3) of the cell's word: the funnel shift takes its amount modulo 32
+          const uint32_t v = __funnelshift_r(word[k], 0u, a << 3);
+          const uint32_t f = v & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
+          int n = static_cast<int>(v & 0x3fu);
+          if (TRAJ) {
+            const int64_t o = (t0 + r) * N + env0 + k * 32 + lane;
+            if (obs) obs[o] = n;
+            if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
+            if (done) done[o] = f ? 1 : 0;
+          }
+          fsum[k] += f;                               // 64*goals + 128*lavas
+          fsq[k] += f * f;                            // 4096*goals + 16384*lavas
+          if (auto_reset && f) n = st[k];
+          p[k] = n;
+          word[k] = tab[n * EPW + k * 32 + lane];
+        }
+      }
+      __syncwarp();                                   // every lane is done with this stage
+      if (lane == 0 && b + kBulkStages < nbatch) issue_batch(b + kBulkStages);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
+      const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
+      const long long dones = static_cast<long long>(goals) + lavas;
+      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
+      rsum += ret;
+      dcnt += dones;
+      const int64_t e = env0 + k * 32 + lane;
+      pos[e] = p[k];
+      if (env_return) env_return[e] = static_cast<int>(ret) + (accumulate ? env_return[e] : 0);
+      if (env_done) env_done[e] = static_cast<int>(dones) + (accumulate ? env_done[e] : 0);
+    }
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
 // ---- rollout over a shared NT16 table -------------------------------------------------------
 constexpr int kNt16Threads = 256;
 
@@ -273,6 +415,26 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
   const TableFormat fmt = table_format(lv);
   const int cells = lv->X * lv->Y;
   const bool traj = obs || reward || done;
+  if (fmt == kTableNT8 && n % kBulkEnvsPerWarp == 0 && start_choice == nullptr && al16(actions) && al16(tables)) {
+    const size_t smem = static_cast<size_t>(kBulkWarps) *
+                        (static_cast<size_t>(cells) * 512 + kBulkStages * kBulkRows * 512);
+    const unsigned blocks = static_cast<unsigned>((n / kBulkEnvsPerWarp + kBulkWarps - 1) / kBulkWarps);
+    if (traj) {
+      cudaError_t e = cudaFuncSetAttribute(rollout_nt8_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      rollout_nt8_bulk_kernel<true><<<blocks, kBulkWarps * 32, smem, st>>>(
+          n, T, cells, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
+    } else {
+      cudaError_t e = cudaFuncSetAttribute(rollout_nt8_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           static_cast<int>(smem));
+      if (e != cudaSuccess) return static_cast<int>(e);
+      rollout_nt8_bulk_kernel<false><<<blocks, kBulkWarps * 32, smem, st>>>(
+          n, T, cells, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
+    }
+    GU_CHECK_LAUNCH();
+    return GU_OK;
+  }
   if (fmt == kTableNT8) {
     const bool vec = (n % 4 == 0) && al16(actions) && al16(pos) && al16(tables) && al16(lv->start) &&
                      (!obs || al16(obs)) && (!reward || al16(reward)) && (!done || al4(done)) &&
