@@ -11,16 +11,25 @@
 //   NT8  (per-env levels, X*Y <= 64):  one 32-bit word per cell, byte a = landing cell of
 //        action a in bits 0-5, goal flag bit 6, lava flag bit 7 (goal cleared when lava is set:
 //        lava wins, griduniverse_env.py:86-90).  WORD-MAJOR uint32[cells][N].
+//   INFO8 (per-env levels, X*Y <= 256, X <= 127): one byte per cell, bits 0-3 = action a moves the
+//        agent (not a grid edge, not a wall, cell not terminal), bit 6 goal, bit 7 lava of the cell
+//        itself; four cells per 32-bit word, WORD-MAJOR uint32[ceil(cells/4)][N].  A quarter of
+//        NT8's footprint, so four times as many envs stay resident per SM.
 //   NT16 (shared level, X*Y <= 16383): uint16 per (cell, action): landing in bits 0-13, goal
 //        bit 14, lava bit 15.  uint16[cells][4], read by every env of the batch.
+#include <cstdlib>
+
 #include "gu_env.cuh"
 
 namespace gu {
 
-enum TableFormat { kTableNone = 0, kTableNT8 = 1, kTableNT16 = 2 };
+enum TableFormat { kTableNone = 0, kTableNT8 = 1, kTableNT16 = 2, kTableINFO8 = 3 };
 
 static TableFormat table_format(const gu_levels* lv) {
   const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
+  static const char* force = getenv("GU_TABLE_FORMAT");   // developer switch for A/B timing
+  if (lv->per_env && cells <= 64 && force && force[0] == 'N') return kTableNT8;
+  if (lv->per_env && cells <= 256 && lv->X <= 127) return kTableINFO8;
   if (lv->per_env && cells <= 64) return kTableNT8;
   if (!lv->per_env && cells <= 16383) return kTableNT16;
   return kTableNone;
@@ -43,6 +52,33 @@ pack_nt8_kernel(LevelsView lv, uint32_t* __restrict__ tables) {
       word |= (static_cast<uint32_t>(n) | f) << (8 * a);
     }
     tables[static_cast<int64_t>(s) * lv.N + env] = word;
+  }
+}
+
+__global__ void __launch_bounds__(128)
+pack_info8_kernel(LevelsView lv, uint32_t* __restrict__ tables) {
+  const int64_t env = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (env >= lv.N) return;
+  const int cells = lv.X * lv.Y;
+  const int words = (cells + 3) / 4;
+  for (int w = 0; w < words; ++w) {
+    uint32_t word = 0;
+    for (int j = 0; j < 4; ++j) {
+      const int s = 4 * w + j;
+      if (s >= cells) break;
+      uint32_t b = 0;
+#pragma unroll
+      for (int a = 0; a < 4; ++a) {
+        int n, r;
+        bool term;
+        transition(lv, env, s, a, true, n, r, term);
+        b |= (n != s ? 1u : 0u) << a;
+      }
+      const bool lava = plane_bit(lv.lava, lv, env, s), goal = plane_bit(lv.goal, lv, env, s);
+      b |= lava ? 0x80u : (goal ? 0x40u : 0u);
+      word |= b << (8 * j);
+    }
+    tables[static_cast<int64_t>(w) * lv.N + env] = word;
   }
 }
 
@@ -340,6 +376,153 @@ rollout_nt8_bulk_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restr
   publish_stats(rsum, dcnt, stats);
 }
 
+// ---- rollout over INFO8 tables, TMA bulk-copy staged ---------------------------------------------
+// Same staging as rollout_nt8_bulk_kernel; a warp owns 32*EPT consecutive envs and lane l steps
+// envs l, l+32, ...  Per step: allowed = bit a of the current cell's info byte, the landing cell
+// is pos + allowed * delta[a] (delta = -X, +1, +X, -1 from a byte LUT), then one shared load
+// fetches the landing cell's info byte, whose goal / lava bits give reward and done.
+constexpr int kInfoRows = 8;       // action rows (time steps) per batch
+constexpr int kInfoStages = 2;
+
+template <int EPT, bool TRAJ>
+__global__ void __launch_bounds__(kBulkWarps * 32)
+rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t* __restrict__ tables,
+                          const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+                          int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                          const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
+                          int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  constexpr int EPW = 32 * EPT, ROWB = EPW * 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t per_warp = static_cast<size_t>(words) * ROWB + kInfoStages * kInfoRows * ROWB;
+  uint8_t* wbase = smem_raw + warp * per_warp;
+  uint32_t* tab = reinterpret_cast<uint32_t*>(wbase);                                   // [words][EPW]
+  uint32_t* act = reinterpret_cast<uint32_t*>(wbase + static_cast<size_t>(words) * ROWB);  // [stages][rows][EPW]
+  __shared__ __align__(8) uint64_t bars[kBulkWarps][kInfoStages + 1];
+  const uint32_t bar_tab = smem_u32(&bars[warp][kInfoStages]);
+  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBulkWarps + warp) * EPW;   // N % EPW == 0
+  const bool live = env0 < N;
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
+  const int64_t nbatch = (T + kInfoRows - 1) / kInfoRows;
+  // signed byte LUT of the four moves: UP -X, RIGHT +1, DOWN +X, LEFT -1
+  const uint32_t deltas = (static_cast<uint32_t>(-X) & 0xffu) | (1u << 8) | ((static_cast<uint32_t>(X) & 0xffu) << 16) |
+                          (0xffu << 24);
+  long long rsum = 0, dcnt = 0;
+
+  if (live) {
+    if (lane == 0) {
+      for (int i = 0; i <= kInfoStages; ++i) mbar_init(smem_u32(&bars[warp][i]), 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue_batch = [&](int64_t b) {          // lane 0 only
+      const int stage = static_cast<int>(b % kInfoStages);
+      const int64_t t0 = b * kInfoRows;
+      const int rows = static_cast<int>(T - t0 < kInfoRows ? T - t0 : kInfoRows);
+      const uint32_t bar = smem_u32(&bars[warp][stage]);
+      mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROWB);
+      for (int r = 0; r < rows; ++r)
+        bulk_g2s(smem_u32(act + (stage * kInfoRows + r) * EPW), actions + (t0 + r) * N + env0, ROWB, bar);
+    };
+    if (lane == 0) {
+      mbar_expect_tx(bar_tab, static_cast<uint32_t>(words) * ROWB);
+      for (int w = 0; w < words; ++w)
+        bulk_g2s(smem_u32(tab + w * EPW), tables + static_cast<int64_t>(w) * N + env0, ROWB, bar_tab);
+      for (int64_t b = 0; b < kInfoStages && b < nbatch; ++b) issue_batch(b);
+    }
+    int p[EPT], st[EPT];
+    uint32_t inf[EPT], inf_st[EPT], fsum[EPT], fsq[EPT];
+    const uint32_t* tabk[EPT];
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      p[k] = pos[env0 + k * 32 + lane];
+      st[k] = start[env0 + k * 32 + lane];
+      fsum[k] = 0;
+      fsq[k] = 0;
+      tabk[k] = tab + k * 32 + lane;
+    }
+    mbar_wait(bar_tab, 0);
+    // info byte of cell c: word c >> 2 of the env's column, byte c & 3 (funnel shift, amount mod 32)
+    auto info_at = [&](int k, int c) -> uint32_t {
+      const uint32_t word = tabk[k][static_cast<uint32_t>(c & ~3) * (EPW / 4)];
+      return __funnelshift_r(word, 0u, static_cast<uint32_t>(c) << 3);
+    };
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      inf[k] = info_at(k, p[k]);
+      inf_st[k] = info_at(k, st[k]);
+    }
+
+    for (int64_t b = 0; b < nbatch; ++b) {
+      const int stage = static_cast<int>(b % kInfoStages);
+      const int64_t t0 = b * kInfoRows;
+      const int rows = static_cast<int>(T - t0 < kInfoRows ? T - t0 : kInfoRows);
+      mbar_wait(smem_u32(&bars[warp][stage]), static_cast<uint32_t>((b / kInfoStages) & 1));
+      const uint32_t* arow = act + stage * kInfoRows * EPW + lane;
+#pragma unroll 4
+      for (int r = 0; r < rows; ++r) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+          const uint32_t a = arow[r * EPW + k * 32] & 3u;
+          const uint32_t allowed = (inf[k] >> a) & 1u;
+          // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
+          int d;
+          asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
+          int n = p[k] + static_cast<int>(allowed) * d;
+          uint32_t i2 = info_at(k, n);
+          const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
+          if (TRAJ) {
+            const int64_t o = (t0 + r) * N + env0 + k * 32 + lane;
+            if (obs) obs[o] = n;
+            if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
+            if (done) done[o] = f ? 1 : 0;
+          }
+          fsum[k] += f;                               // 64*goals + 128*lavas
+          fsq[k] += f * f;                            // 4096*goals + 16384*lavas
+          if (auto_reset && f) { n = st[k]; i2 = inf_st[k]; }
+          p[k] = n;
+          inf[k] = i2;
+        }
+      }
+      __syncwarp();                                   // every lane is done with this stage
+      if (lane == 0 && b + kInfoStages < nbatch) issue_batch(b + kInfoStages);
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+      const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
+      const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
+      const long long dones = static_cast<long long>(goals) + lavas;
+      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
+      rsum += ret;
+      dcnt += dones;
+      const int64_t e = env0 + k * 32 + lane;
+      pos[e] = p[k];
+      if (env_return) env_return[e] = static_cast<int>(ret) + (accumulate ? env_return[e] : 0);
+      if (env_done) env_done[e] = static_cast<int>(dones) + (accumulate ? env_done[e] : 0);
+    }
+  }
+  publish_stats(rsum, dcnt, stats);
+}
+
+template <int EPT, bool TRAJ>
+static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
+                        int32_t* reward, uint8_t* done, int32_t* env_return, int32_t* env_done, int64_t* stats,
+                        const uint32_t* tables, uint32_t flags, cudaStream_t st) {
+  const int cells = lv->X * lv->Y, words = (cells + 3) / 4;
+  constexpr int EPW = 32 * EPT;
+  const size_t smem = static_cast<size_t>(kBulkWarps) * (static_cast<size_t>(words) + kInfoStages * kInfoRows) * EPW * 4;
+  const unsigned blocks = static_cast<unsigned>((n / EPW + kBulkWarps - 1) / kBulkWarps);
+  cudaError_t e = cudaFuncSetAttribute(rollout_info8_bulk_kernel<EPT, TRAJ>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  rollout_info8_bulk_kernel<EPT, TRAJ><<<blocks, kBulkWarps * 32, smem, st>>>(
+      n, T, lv->X, words, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
+  cudaError_t le = cudaGetLastError();
+  return le == cudaSuccess ? GU_OK : static_cast<int>(le);
+}
+
 // ---- rollout over a shared NT16 table -------------------------------------------------------
 constexpr int kNt16Threads = 256;
 
@@ -415,6 +598,23 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
   const TableFormat fmt = table_format(lv);
   const int cells = lv->X * lv->Y;
   const bool traj = obs || reward || done;
+  if (fmt == kTableINFO8) {
+    if (start_choice != nullptr || !al16(actions) || !al16(tables) || n % 32 != 0) return GU_ERR_UNSUPPORTED;
+    // envs per lane: 4 when that still gives every SM a dozen warps, else fewer so small batches spread out
+    static const char* force = getenv("GU_INFO8_EPT");
+    int ept = (n % 128 == 0 && n / 128 >= 148 * 12) ? 4 : ((n % 64 == 0 && n / 64 >= 148 * 12) ? 2 : 1);
+    if (force) ept = atoi(force);
+    if (n % (32 * ept) != 0) return GU_ERR_UNSUPPORTED;
+#define GU_INFO8(EPT)                                                                                              \
+  return traj ? launch_info8<EPT, true>(lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats,    \
+                                        tables, flags, st)                                                        \
+              : launch_info8<EPT, false>(lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats,   \
+                                         tables, flags, st)
+    if (ept == 4) GU_INFO8(4);
+    if (ept == 2) GU_INFO8(2);
+    GU_INFO8(1);
+#undef GU_INFO8
+  }
   if (fmt == kTableNT8 && n % kBulkEnvsPerWarp == 0 && start_choice == nullptr && al16(actions) && al16(tables)) {
     const size_t smem = static_cast<size_t>(kBulkWarps) *
                         (static_cast<size_t>(cells) * 512 + kBulkStages * kBulkRows * 512);
@@ -495,6 +695,7 @@ extern "C" __attribute__((visibility("default"))) int64_t gu_tables_bytes(const 
   const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
   switch (table_format(lv)) {
     case kTableNT8: return cells * 4 * n;
+    case kTableINFO8: return ((cells + 3) / 4) * 4 * n;
     case kTableNT16: return cells * 8;
     default: return 0;
   }
@@ -511,6 +712,9 @@ extern "C" __attribute__((visibility("default"))) int gu_pack_tables(const gu_le
   if (fmt == kTableNT8) {
     if (n == 0) return GU_OK;
     pack_nt8_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(view_of(lv, n), tables);
+  } else if (fmt == kTableINFO8) {
+    if (n == 0) return GU_OK;
+    pack_info8_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(view_of(lv, n), tables);
   } else if (fmt == kTableNT16) {
     const int cells = lv->X * lv->Y;
     pack_nt16_kernel<<<(cells * 4 + 127) / 128, 128, 0, st>>>(view_of(lv, 1), reinterpret_cast<uint16_t*>(tables));
