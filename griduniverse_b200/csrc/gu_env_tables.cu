@@ -384,7 +384,13 @@ rollout_nt8_bulk_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restr
 constexpr int kInfoRows = 8;       // action rows (time steps) per batch
 constexpr int kInfoStages = 2;
 
-template <int EPT, bool TRAJ>
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+
+template <int EPT, bool TRAJ, bool AUTO_RESET>
 __global__ void __launch_bounds__(kBulkWarps * 32)
 rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t* __restrict__ tables,
                           const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
@@ -402,7 +408,6 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
   const uint32_t bar_tab = smem_u32(&bars[warp][kInfoStages]);
   const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBulkWarps + warp) * EPW;   // N % EPW == 0
   const bool live = env0 < N;
-  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
   const bool accumulate = flags & GU_FLAG_ACCUMULATE;
   const int64_t nbatch = (T + kInfoRows - 1) / kInfoRows;
   // signed byte LUT of the four moves: UP -X, RIGHT +1, DOWN +X, LEFT -1
@@ -434,19 +439,20 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
     }
     int p[EPT], st[EPT];
     uint32_t inf[EPT], inf_st[EPT], fsum[EPT], fsq[EPT];
-    const uint32_t* tabk[EPT];
+    uint32_t tabk[EPT];                              // shared-memory byte address of the env's column
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       p[k] = pos[env0 + k * 32 + lane];
       st[k] = start[env0 + k * 32 + lane];
       fsum[k] = 0;
       fsq[k] = 0;
-      tabk[k] = tab + k * 32 + lane;
+      tabk[k] = smem_u32(tab + k * 32 + lane);
     }
     mbar_wait(bar_tab, 0);
-    // info byte of cell c: word c >> 2 of the env's column, byte c & 3 (funnel shift, amount mod 32)
+    // info byte of cell c: word c >> 2 of the env's column (rows are ROWB bytes apart), byte c & 3
+    // (funnel shift, amount taken modulo 32)
     auto info_at = [&](int k, int c) -> uint32_t {
-      const uint32_t word = tabk[k][static_cast<uint32_t>(c & ~3) * (EPW / 4)];
+      const uint32_t word = lds_u32(tabk[k] + (static_cast<uint32_t>(c) & ~3u) * (ROWB / 4));
       return __funnelshift_r(word, 0u, static_cast<uint32_t>(c) << 3);
     };
 #pragma unroll
@@ -470,7 +476,8 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
           // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
           int d;
           asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
-          int n = p[k] + static_cast<int>(allowed) * d;
+          int n;
+          asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
           uint32_t i2 = info_at(k, n);
           const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
           if (TRAJ) {
@@ -481,7 +488,7 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
           }
           fsum[k] += f;                               // 64*goals + 128*lavas
           fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-          if (auto_reset && f) { n = st[k]; i2 = inf_st[k]; }
+          if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
           p[k] = n;
           inf[k] = i2;
         }
@@ -506,7 +513,7 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
   publish_stats(rsum, dcnt, stats);
 }
 
-template <int EPT, bool TRAJ>
+template <int EPT, bool TRAJ, bool AR>
 static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
                         int32_t* reward, uint8_t* done, int32_t* env_return, int32_t* env_done, int64_t* stats,
                         const uint32_t* tables, uint32_t flags, cudaStream_t st) {
@@ -514,10 +521,10 @@ static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t
   constexpr int EPW = 32 * EPT;
   const size_t smem = static_cast<size_t>(kBulkWarps) * (static_cast<size_t>(words) + kInfoStages * kInfoRows) * EPW * 4;
   const unsigned blocks = static_cast<unsigned>((n / EPW + kBulkWarps - 1) / kBulkWarps);
-  cudaError_t e = cudaFuncSetAttribute(rollout_info8_bulk_kernel<EPT, TRAJ>,
+  cudaError_t e = cudaFuncSetAttribute(rollout_info8_bulk_kernel<EPT, TRAJ, AR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  rollout_info8_bulk_kernel<EPT, TRAJ><<<blocks, kBulkWarps * 32, smem, st>>>(
+  rollout_info8_bulk_kernel<EPT, TRAJ, AR><<<blocks, kBulkWarps * 32, smem, st>>>(
       n, T, lv->X, words, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
   cudaError_t le = cudaGetLastError();
   return le == cudaSuccess ? GU_OK : static_cast<int>(le);
@@ -605,15 +612,18 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
     int ept = (n % 128 == 0 && n / 128 >= 148 * 12) ? 4 : ((n % 64 == 0 && n / 64 >= 148 * 12) ? 2 : 1);
     if (force) ept = atoi(force);
     if (n % (32 * ept) != 0) return GU_ERR_UNSUPPORTED;
-#define GU_INFO8(EPT)                                                                                              \
-  return traj ? launch_info8<EPT, true>(lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats,    \
-                                        tables, flags, st)                                                        \
-              : launch_info8<EPT, false>(lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats,   \
-                                         tables, flags, st)
+    const bool ar = flags & GU_FLAG_AUTO_RESET;
+#define GU_INFO8_ARGS lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats, tables, flags, st
+#define GU_INFO8(EPT)                                                                              \
+  return traj ? (ar ? launch_info8<EPT, true, true>(GU_INFO8_ARGS)                                 \
+                    : launch_info8<EPT, true, false>(GU_INFO8_ARGS))                               \
+              : (ar ? launch_info8<EPT, false, true>(GU_INFO8_ARGS)                                \
+                    : launch_info8<EPT, false, false>(GU_INFO8_ARGS))
     if (ept == 4) GU_INFO8(4);
     if (ept == 2) GU_INFO8(2);
     GU_INFO8(1);
 #undef GU_INFO8
+#undef GU_INFO8_ARGS
   }
   if (fmt == kTableNT8 && n % kBulkEnvsPerWarp == 0 && start_choice == nullptr && al16(actions) && al16(tables)) {
     const size_t smem = static_cast<size_t>(kBulkWarps) *
