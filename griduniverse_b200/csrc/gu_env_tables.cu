@@ -17,6 +17,8 @@
 //        NT8's footprint, so four times as many envs stay resident per SM.
 //   NT16 (shared level, X*Y <= 16383): uint16 per (cell, action): landing in bits 0-13, goal
 //        bit 14, lava bit 15.  uint16[cells][4], read by every env of the batch.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "gu_env.cuh"
@@ -376,12 +378,19 @@ rollout_nt8_bulk_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restr
   publish_stats(rsum, dcnt, stats);
 }
 
-// ---- rollout over INFO8 tables, TMA bulk-copy staged ---------------------------------------------
-// Same staging as rollout_nt8_bulk_kernel; a warp owns 32*EPT consecutive envs and lane l steps
-// envs l, l+32, ...  Per step: allowed = bit a of the current cell's info byte, the landing cell
-// is pos + allowed * delta[a] (delta = -X, +1, +X, -1 from a byte LUT), then one shared load
-// fetches the landing cell's info byte, whose goal / lava bits give reward and done.
-constexpr int kInfoRows = 8;       // action rows (time steps) per batch
+// ---- rollout over INFO8 tables, TMA-tiled staging ---------------------------------------------------
+// A warp owns 32*EPT consecutive envs and lane l steps envs l, l+32, ...  All HBM traffic is 2-D
+// TMA tile copies (cp.async.bulk.tensor, SASS UTMALDG) issued by one elected lane and completed
+// on per-warp mbarriers: the env range's info table once ([words x EPW] box of the
+// [words][N] table), then the action stream as [kInfoRows x EPW] boxes of the [T][N] action
+// matrix through a kInfoStages-deep ring, so several KB per warp are always in flight while the
+// lanes step.  Tiles land in shared memory exactly as stored, and lane l only ever reads column
+// k*32+l, so every shared load of a warp hits 32 different banks.  No block-level barrier.
+//
+// Per step: allowed = bit a of the current cell's info byte, the landing cell is
+// pos + allowed * delta[a] (delta = -X, +1, +X, -1 from a byte LUT), then one shared load fetches
+// the landing cell's info byte, whose goal / lava bits give reward and done (griduniverse_env.py:155).
+constexpr int kInfoRows = 8;       // action rows (time steps) per TMA box
 constexpr int kInfoStages = 2;
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
@@ -389,53 +398,56 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
 
 template <int EPT, bool TRAJ, bool AUTO_RESET>
 __global__ void __launch_bounds__(kBulkWarps * 32)
-rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t* __restrict__ tables,
-                          const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
-                          int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
-                          const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
-                          int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
+rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap tab_map,
+                         int N, int T, int X, int words, int32_t* __restrict__ pos, int32_t* __restrict__ obs,
+                         int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                         const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
+                         int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int EPW = 32 * EPT, ROWB = EPW * 4;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t per_warp = static_cast<size_t>(words) * ROWB + kInfoStages * kInfoRows * ROWB;
-  uint8_t* wbase = smem_raw + warp * per_warp;
-  uint32_t* tab = reinterpret_cast<uint32_t*>(wbase);                                   // [words][EPW]
-  uint32_t* act = reinterpret_cast<uint32_t*>(wbase + static_cast<size_t>(words) * ROWB);  // [stages][rows][EPW]
+  constexpr uint32_t kBoxBytes = kInfoRows * ROWB;
+  const int lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);       // warp-uniform for the TMA operands
+  const uint32_t per_warp = (static_cast<uint32_t>(words) + kInfoStages * kInfoRows) * ROWB;
+  const uint32_t tab_s = ((smem_u32(smem_raw) + 127u) & ~127u) + warp * per_warp;   // [words][EPW] words
+  const uint32_t act_s = tab_s + static_cast<uint32_t>(words) * ROWB;      // [stages][rows][EPW] words
   __shared__ __align__(8) uint64_t bars[kBulkWarps][kInfoStages + 1];
-  const uint32_t bar_tab = smem_u32(&bars[warp][kInfoStages]);
-  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBulkWarps + warp) * EPW;   // N % EPW == 0
-  const bool live = env0 < N;
+  const uint32_t bar0 = smem_u32(&bars[warp][0]);
+  const uint32_t bar_tab = bar0 + 8 * kInfoStages;
+  const int env0 = (blockIdx.x * kBulkWarps + warp) * EPW;               // N % EPW == 0
   const bool accumulate = flags & GU_FLAG_ACCUMULATE;
-  const int64_t nbatch = (T + kInfoRows - 1) / kInfoRows;
+  const int nbatch = (T + kInfoRows - 1) / kInfoRows;
   // signed byte LUT of the four moves: UP -X, RIGHT +1, DOWN +X, LEFT -1
   const uint32_t deltas = (static_cast<uint32_t>(-X) & 0xffu) | (1u << 8) | ((static_cast<uint32_t>(X) & 0xffu) << 16) |
                           (0xffu << 24);
   long long rsum = 0, dcnt = 0;
 
-  if (live) {
-    if (lane == 0) {
-      for (int i = 0; i <= kInfoStages; ++i) mbar_init(smem_u32(&bars[warp][i]), 1);
+  if (env0 < N) {
+    if (elect_one()) {
+      for (int i = 0; i <= kInfoStages; ++i) mbar_init(bar0 + 8 * i, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     __syncwarp();
-    auto issue_batch = [&](int64_t b) {          // lane 0 only
-      const int stage = static_cast<int>(b % kInfoStages);
-      const int64_t t0 = b * kInfoRows;
-      const int rows = static_cast<int>(T - t0 < kInfoRows ? T - t0 : kInfoRows);
-      const uint32_t bar = smem_u32(&bars[warp][stage]);
-      mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROWB);
-      for (int r = 0; r < rows; ++r)
-        bulk_g2s(smem_u32(act + (stage * kInfoRows + r) * EPW), actions + (t0 + r) * N + env0, ROWB, bar);
-    };
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_expect_tx(bar_tab, static_cast<uint32_t>(words) * ROWB);
-      for (int w = 0; w < words; ++w)
-        bulk_g2s(smem_u32(tab + w * EPW), tables + static_cast<int64_t>(w) * N + env0, ROWB, bar_tab);
-      for (int64_t b = 0; b < kInfoStages && b < nbatch; ++b) issue_batch(b);
+      tma_load_2d(tab_s, &tab_map, env0, 0, bar_tab);
+      for (int b = 0; b < kInfoStages && b < nbatch; ++b) {
+        mbar_expect_tx(bar0 + 8 * b, kBoxBytes);
+        tma_load_2d(act_s + b * kBoxBytes, &act_map, env0, b * kInfoRows, bar0 + 8 * b);
+      }
     }
     int p[EPT], st[EPT];
     uint32_t inf[EPT], inf_st[EPT], fsum[EPT], fsq[EPT];
@@ -446,7 +458,7 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
       st[k] = start[env0 + k * 32 + lane];
       fsum[k] = 0;
       fsq[k] = 0;
-      tabk[k] = smem_u32(tab + k * 32 + lane);
+      tabk[k] = tab_s + (k * 32 + lane) * 4;
     }
     mbar_wait(bar_tab, 0);
     // info byte of cell c: word c >> 2 of the env's column (rows are ROWB bytes apart), byte c & 3
@@ -461,50 +473,59 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
       inf_st[k] = info_at(k, st[k]);
     }
 
-    for (int64_t b = 0; b < nbatch; ++b) {
-      const int stage = static_cast<int>(b % kInfoStages);
-      const int64_t t0 = b * kInfoRows;
-      const int rows = static_cast<int>(T - t0 < kInfoRows ? T - t0 : kInfoRows);
-      mbar_wait(smem_u32(&bars[warp][stage]), static_cast<uint32_t>((b / kInfoStages) & 1));
-      const uint32_t* arow = act + stage * kInfoRows * EPW + lane;
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
+    auto step_row = [&](uint32_t arow, int t) {      // arow: smem address of this lane's word in the action row
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) {
-          const uint32_t a = arow[r * EPW + k * 32] & 3u;
-          const uint32_t allowed = (inf[k] >> a) & 1u;
-          // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
-          int d;
-          asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
-          int n;
-          asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
-          uint32_t i2 = info_at(k, n);
-          const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
-          if (TRAJ) {
-            const int64_t o = (t0 + r) * N + env0 + k * 32 + lane;
-            if (obs) obs[o] = n;
-            if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
-            if (done) done[o] = f ? 1 : 0;
-          }
-          fsum[k] += f;                               // 64*goals + 128*lavas
-          fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-          if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
-          p[k] = n;
-          inf[k] = i2;
+      for (int k = 0; k < EPT; ++k) {
+        const uint32_t a = lds_u32(arow + k * 128) & 3u;
+        const uint32_t allowed = (inf[k] >> a) & 1u;
+        // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
+        int d, n;
+        asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
+        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
+        uint32_t i2 = info_at(k, n);
+        const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
+        if (TRAJ) {
+          const int64_t o = static_cast<int64_t>(t) * N + env0 + k * 32 + lane;
+          if (obs) obs[o] = n;
+          if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
+          if (done) done[o] = f ? 1 : 0;
         }
+        fsum[k] += f;                               // 64*goals + 128*lavas
+        fsq[k] += f * f;                            // 4096*goals + 16384*lavas
+        if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
+        p[k] = n;
+        inf[k] = i2;
+      }
+    };
+
+    int stage = 0;
+    uint32_t parity = 0;
+    for (int b = 0; b < nbatch; ++b) {
+      const int t0 = b * kInfoRows;
+      mbar_wait(bar0 + 8 * stage, parity);
+      const uint32_t arow = act_s + stage * kBoxBytes + lane * 4;
+      if (t0 + kInfoRows <= T) {
+#pragma unroll
+        for (int r = 0; r < kInfoRows; ++r) step_row(arow + r * ROWB, t0 + r);
+      } else {
+        for (int r = 0; t0 + r < T; ++r) step_row(arow + r * ROWB, t0 + r);   // rows past T are zero fill
       }
       __syncwarp();                                   // every lane is done with this stage
-      if (lane == 0 && b + kInfoStages < nbatch) issue_batch(b + kInfoStages);
+      if (b + kInfoStages < nbatch && elect_one()) {
+        mbar_expect_tx(bar0 + 8 * stage, kBoxBytes);
+        tma_load_2d(act_s + stage * kBoxBytes, &act_map, env0, (b + kInfoStages) * kInfoRows, bar0 + 8 * stage);
+      }
+      if (++stage == kInfoStages) { stage = 0; parity ^= 1u; }
     }
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
       const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
       const long long dones = static_cast<long long>(goals) + lavas;
-      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
+      const long long ret = -(static_cast<long long>(T) - dones) + 10ll * goals - 10ll * lavas;
       rsum += ret;
       dcnt += dones;
-      const int64_t e = env0 + k * 32 + lane;
+      const int e = env0 + k * 32 + lane;
       pos[e] = p[k];
       if (env_return) env_return[e] = static_cast<int>(ret) + (accumulate ? env_return[e] : 0);
       if (env_done) env_done[e] = static_cast<int>(dones) + (accumulate ? env_done[e] : 0);
@@ -513,19 +534,51 @@ rollout_info8_bulk_kernel(int64_t N, int64_t T, int X, int words, const uint32_t
   publish_stats(rsum, dcnt, stats);
 }
 
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time libcuda dependency)
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D map of a row-major int32 [rows][cols] matrix, box = [box_rows][box_cols], out-of-range rows zero-filled
+static bool make_map_i32(CUtensorMap* map, const void* base, int64_t rows, int64_t cols, int box_rows, int box_cols) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  const cuuint64_t strides[1] = {static_cast<cuuint64_t>(cols) * 4};
+  const cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int EPT, bool TRAJ, bool AR>
 static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
                         int32_t* reward, uint8_t* done, int32_t* env_return, int32_t* env_done, int64_t* stats,
                         const uint32_t* tables, uint32_t flags, cudaStream_t st) {
   const int cells = lv->X * lv->Y, words = (cells + 3) / 4;
   constexpr int EPW = 32 * EPT;
-  const size_t smem = static_cast<size_t>(kBulkWarps) * (static_cast<size_t>(words) + kInfoStages * kInfoRows) * EPW * 4;
+  CUtensorMap act_map, tab_map;
+  if (!make_map_i32(&act_map, actions, T, n, kInfoRows, EPW) || !make_map_i32(&tab_map, tables, words, n, words, EPW))
+    return GU_ERR_UNSUPPORTED;
+  const size_t smem = static_cast<size_t>(kBulkWarps) * (static_cast<size_t>(words) + kInfoStages * kInfoRows) * EPW * 4 + 128;
   const unsigned blocks = static_cast<unsigned>((n / EPW + kBulkWarps - 1) / kBulkWarps);
-  cudaError_t e = cudaFuncSetAttribute(rollout_info8_bulk_kernel<EPT, TRAJ, AR>,
+  cudaError_t e = cudaFuncSetAttribute(rollout_info8_tma_kernel<EPT, TRAJ, AR>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  rollout_info8_bulk_kernel<EPT, TRAJ, AR><<<blocks, kBulkWarps * 32, smem, st>>>(
-      n, T, lv->X, words, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
+  rollout_info8_tma_kernel<EPT, TRAJ, AR><<<blocks, kBulkWarps * 32, smem, st>>>(
+      act_map, tab_map, static_cast<int>(n), static_cast<int>(T), lv->X, words, pos, obs, reward, done, lv->start,
+      env_return, env_done, stats, flags);
   cudaError_t le = cudaGetLastError();
   return le == cudaSuccess ? GU_OK : static_cast<int>(le);
 }
@@ -606,10 +659,12 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
   const int cells = lv->X * lv->Y;
   const bool traj = obs || reward || done;
   if (fmt == kTableINFO8) {
-    if (start_choice != nullptr || !al16(actions) || !al16(tables) || n % 32 != 0) return GU_ERR_UNSUPPORTED;
-    // envs per lane: 4 when that still gives every SM a dozen warps, else fewer so small batches spread out
+    if (start_choice != nullptr || !al16(actions) || !al16(tables) || n % 32 != 0 || n >= (1ll << 31))
+      return GU_ERR_UNSUPPORTED;
+    // envs per lane: 2 when that still gives every SM a dozen warps (measured best on B200 for large
+    // batches), else 1 so small batches spread over all SMs; 4 only on request
     static const char* force = getenv("GU_INFO8_EPT");
-    int ept = (n % 128 == 0 && n / 128 >= 148 * 12) ? 4 : ((n % 64 == 0 && n / 64 >= 148 * 12) ? 2 : 1);
+    int ept = (n % 64 == 0 && n / 64 >= 148 * 12) ? 2 : 1;
     if (force) ept = atoi(force);
     if (n % (32 * ept) != 0) return GU_ERR_UNSUPPORTED;
     const bool ar = flags & GU_FLAG_AUTO_RESET;
