@@ -51,12 +51,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def profiled_traffic(key):
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (or None)."""
+def profiled_traffic(key, share=1.0):
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (taken at the
+    single-GPU shape; `share` = this launch's fraction of those units), or None."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as f:
-            return json.load(f).get(key)
+            v = json.load(f).get(key)
+        return None if v is None else v * share
     return None
 
 
@@ -338,7 +340,7 @@ def run_ours(args):
             "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": env_config(world),
             "roofline": {"bound": "hbm", "achieved": env_achieved, "peak": peak, "unit": "GB/s",
-                         "frac": env_achieved / peak, "traffic": profiled_traffic("rollout_cfg4"),
+                         "frac": env_achieved / peak, "traffic": profiled_traffic("rollout_cfg4", n_local / float(ENV_TOTAL)),
                          "kernel": "rollout (gu_rollout), 4 B/step x %d envs x %d steps per launch" % (n_local, ENV_T),
                          "peak_source": peak_src},
             "e2e": {"value": env_e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_io["h2d"] * world,
@@ -356,7 +358,7 @@ def run_ours(args):
                            "parallelism": "row-sharded x%d, halo send/recv + residual MAX all-reduce per sweep" % world,
                            "l2": "inputs larger than L2 (%.2f GB of V per GPU)" % ((r1 - r0) * VI_SIZE * 4 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": vi_achieved, "peak": peak, "unit": "GB/s",
-                             "frac": vi_achieved / peak, "traffic": profiled_traffic("sweep_greedy_f32_cfg5"),
+                             "frac": vi_achieved / peak, "traffic": profiled_traffic("sweep_greedy_f32_cfg5", (r1 - r0) / float(VI_SIZE)),
                              "kernel": "fused-greedy sweep (gu_sweep_f32, GU_POLICY_GREEDY), 8.375 B/cell",
                              "ms_per_launch": 1000.0 * t_sw, "peak_source": peak_src},
                 "e2e": {"value": vi_e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": io["h2d"] * world,
