@@ -150,9 +150,9 @@ extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* l
                        uint32_t flags, void* stream) {
   int rc = check_levels(lv, n);
   if (rc) return rc;
+  if (n == 0) return GU_OK;
   if (!actions || !pos) return GU_ERR_NULL;
   if ((flags & GU_FLAG_AUTO_RESET) && !start_choice && !lv->start) return GU_ERR_NULL;
-  if (n == 0) return GU_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const LevelsView v = view_of(lv, n);
   const bool vec = (n % 4 == 0) && aligned16(actions) && aligned16(pos) && (!obs || aligned16(obs)) &&
@@ -175,10 +175,10 @@ extern "C" __attribute__((visibility("default"))) int gu_rollout(const gu_levels
                           uint32_t flags, void* stream) {
   int rc = check_levels(lv, n);
   if (rc) return rc;
-  if (!actions || !pos) return GU_ERR_NULL;
   if (T < 0) return GU_ERR_SHAPE;
+  if (n == 0 || T == 0) return GU_OK;      // nothing to do: empty action matrices may be NULL
+  if (!actions || !pos) return GU_ERR_NULL;
   if ((flags & GU_FLAG_AUTO_RESET) && !start_choice && !lv->start) return GU_ERR_NULL;
-  if (n == 0 || T == 0) return GU_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (tables) {
     rc = rollout_tables(lv, n, T, actions, pos, obs, reward, done, start_choice, env_return, env_done,

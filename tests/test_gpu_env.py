@@ -183,3 +183,48 @@ def test_shared_level_many_envs_device_tensors(golden_levels):
     assert np.array_equal(out["obs"].cpu().numpy(), eo) and np.array_equal(out["reward"].cpu().numpy(), er)
     assert np.array_equal(out["pos"].cpu().numpy(), ep)
     assert env.done_count == int(ed.sum()) and env.episode_return_sum == int(er.sum())
+
+
+def test_empty_and_degenerate_batches():
+    """T = 0 leaves the envs where they are; a 1 x N corridor and a single-cell-high grid work."""
+    env = GridUniverseVecEnv(256, grid_shape=(8, 8), auto_reset=True)
+    before = env.pos.clone()
+    out = env.rollout(torch.zeros((0, 256), dtype=torch.int32, device="cuda"), trajectories=True)
+    assert torch.equal(out["pos"], before) and out["obs"].shape == (0, 256)
+    # corridor 9 x 1: goal at the right end, lava at cell 2, walls nowhere
+    lv = orc.Level(9, 1, goals=[8], lavas=[2])
+    env = GridUniverseVecEnv(64, grid_shape=(9, 1), goal_states=[8], lava_states=[2], auto_reset=False)
+    acts = np.random.RandomState(3).randint(0, 4, (50, 64)).astype(np.int32)
+    out = env.rollout(acts, trajectories=True)
+    eo, er, ed, ep = orc.rollout(lv, np.zeros(64, np.int64), acts, auto_reset=False)
+    assert np.array_equal(out["obs"], eo) and np.array_equal(out["reward"], er) and np.array_equal(out["pos"], ep)
+
+
+def test_maximum_table_shapes():
+    """Largest shapes of each table format: 16 x 16 per-env (INFO8), 127-wide rows, 120 x 120 shared (NT16)."""
+    for (X, Y, n) in ((16, 16, 256), (127, 2, 64), (2, 127, 64)):
+        rs = np.random.RandomState(X)
+        cells = X * Y
+        wall = rs.rand(n, cells) < 0.15
+        goal = np.zeros((n, cells), bool)
+        goal[np.arange(n), rs.randint(0, cells, n)] = True
+        wall &= ~goal
+        lava = (rs.rand(n, cells) < 0.03) & ~wall & ~goal
+        start = np.array([int(np.flatnonzero(~wall[i] & ~goal[i] & ~lava[i])[0]) for i in range(n)], np.int32)
+        levels = [Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+        olevels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+        acts = rs.randint(0, 4, (80, n)).astype(np.int32)
+        eo, er, ed, ep = orc.rollout(olevels, start, acts, auto_reset=True)
+        env = GridUniverseVecEnv(n, levels=levels, auto_reset=True)
+        assert env.levels.tables is not None
+        out = env.rollout(acts, trajectories=True)
+        assert np.array_equal(out["obs"], eo) and np.array_equal(out["done"].astype(bool), ed)
+        assert np.array_equal(out["env_return"], er.sum(axis=0))
+    lvl = synth.maze_level(120, 120, seed=4)
+    olv = orc.Level.from_masks(120, 120, lvl.wall, lvl.goal, lvl.lava, lvl.starting_states)
+    env = GridUniverseVecEnv(512, levels=EnvLevels.shared(lvl), auto_reset=True)
+    assert env.levels.tables is not None
+    acts = np.random.RandomState(0).randint(0, 4, (200, 512)).astype(np.int32)
+    out = env.rollout(acts, trajectories=True)
+    eo, er, ed, ep = orc.rollout(olv, np.full(512, lvl.starting_states[0]), acts, auto_reset=True)
+    assert np.array_equal(out["obs"], eo) and np.array_equal(out["reward"], er) and np.array_equal(out["pos"], ep)

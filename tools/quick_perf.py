@@ -20,6 +20,7 @@ size = int(os.environ.get("SIZE", "16384"))
 if what in ("all", "sweep"):
     for dt, bpc in ((np.float32, 8.375), (np.float64, 16.375)):
         if os.environ.get('ONLY') == 'f32' and dt != np.float32: continue
+        if os.environ.get('ONLY') == 'f64' and dt != np.float64: continue
         grid = synth.maze_plan_grid(size, size, seed=0, dtype=dt)
         pl = Planner(None, dt, "cuda", grid=grid)
         a, b = grid.empty(), grid.empty()

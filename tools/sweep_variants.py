@@ -3,7 +3,7 @@ import itertools, os, subprocess, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "griduniverse_b200", "lib", "variants")
-GRID = {"GU_TILED_MIN_BLOCKS": [1, 5, 6], "GU_TILED_PREFETCH_ROWS": [2, 3, 4], "GU_TILED_ROWS_PER_BLOCK": [24, 48]}
+GRID = {"GU_TILED_NV_F64": [1, 2]}
 def variants():
     keys = sorted(GRID)
     for vals in itertools.product(*[GRID[k] for k in keys]):
@@ -21,8 +21,8 @@ if sys.argv[1] == "build":
 else:
     for d in variants():
         name = "_".join(x.split("=")[1] for x in d)
-        env = dict(os.environ, GU_B200_LIB=os.path.join(VDIR, "libgu_%s.so" % name), ONLY="f32")
+        env = dict(os.environ, GU_B200_LIB=os.path.join(VDIR, "libgu_%s.so" % name), ONLY="f64")
         out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_perf.py"), "sweep"], env=env,
                              capture_output=True, text=True).stdout
         print(" ".join(d))
-        print("\n".join(l for l in out.splitlines() if "greedy " in l or "uniform" in l))
+        print("\n".join(l for l in out.splitlines() if "float64" in l))
