@@ -275,13 +275,7 @@ def run_ours(args):
     r0, r1 = shard_rows(VI_SIZE, world, rank)
     grid = synth.maze_plan_grid(VI_SIZE, VI_SIZE, seed=0, dtype=np.float32, device=dev, row_begin=r0, row_end=r1)
     pl = Planner(None, np.float32, dev, grid=grid)
-    if world == 1:
-        class _Solo(ShardedValueIteration):          # same driver, no process group needed
-            def __init__(self, planner):
-                self.pl, self.group, self.rank, self.world, self.collectives = planner, None, 0, 1, 0
-        svi = _Solo(pl)
-    else:
-        svi = ShardedValueIteration(pl)
+    svi = ShardedValueIteration(pl, solo=(world == 1))
     vi_meta = {}
 
     def vi_pass():

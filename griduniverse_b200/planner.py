@@ -60,6 +60,8 @@ class Planner(object):
         ``"uniform"`` / ``"greedy"`` need no array.  A NumPy [N,4] array that is uniform on a
         subset in every row (policy0 of the examples, any greedy policy) is shipped as 1-byte
         tie masks; anything else as T[N,4] probabilities."""
+        if isinstance(policy, tuple):          # already staged: (kind, tensor)
+            return policy
         if isinstance(policy, str):
             return _KINDS[policy], None
         if torch.is_tensor(policy):
@@ -99,7 +101,7 @@ class Planner(object):
 
     # ------------------------------------------------------------------ value iteration
     def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                        discount_factor=1.0, chunk=16, allow_small=True):
+                        discount_factor=1.0, chunk=16, allow_small=True, use_graph=True):
         """dynamic_programming.py:8-28.  Returns (V_padded, tie_masks_padded, sweeps, last_delta).
 
         The first sweep evaluates the caller's policy, every later sweep is the fused
@@ -122,29 +124,11 @@ class Planner(object):
             _cabi.check("gu_vi_small_f64", rc)
             self.launches += 1
             return v_out, tie, int(meta_i.item()), float(meta_d.item())
-        thr = self.np_dtype.type(threshold)
-        bufs = [v0, g.empty()]
-        res = self.new_residuals(max(max_steps, 1))
-        k, sweeps, last = 0, 0, float("nan")
-        converged = False
-        while k < max_steps and not converged:
-            n = min(chunk, max_steps - k)
-            for _ in range(n):
-                self.sweep(bufs[k % 2], bufs[(k + 1) % 2], kind0 if k == 0 else _cabi.GU_POLICY_GREEDY,
-                           pol_t if k == 0 else None, discount_factor, res[k:k + 1],
-                           res[k - 1:k] if k > 0 else None, threshold)
-                k += 1
-            r = res[k - n:k].cpu().numpy()
-            hit = np.flatnonzero(r < thr)
-            if hit.size:
-                sweeps = k - n + int(hit[0]) + 1
-                last = float(r[hit[0]])
-                converged = True
-            else:
-                sweeps, last = k, float(r[-1])
-        v = bufs[sweeps % 2]
-        tie = self.greedy(v, discount_factor)
-        return v, tie, sweeps, last
+        from .sharded import ShardedValueIteration      # one driver for one GPU and for row shards
+        if getattr(self, "_solo_driver", None) is None:
+            self._solo_driver = ShardedValueIteration(self, solo=True)
+        return self._solo_driver.value_iteration((kind0, pol_t), v0, threshold, max_steps, discount_factor,
+                                                 chunk=chunk, use_graph=use_graph)
 
     # ------------------------------------------------------------------ policy iteration
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,

@@ -34,15 +34,18 @@ class ShardedValueIteration(object):
     ``greedy``, ``new_residuals``, ``stage_policy``, ``stage_value`` and ``np_dtype`` -- the
     CUDA ``Planner`` in production, a CPU stand-in in the gloo tests of the host logic."""
 
-    def __init__(self, planner, group=None):
+    def __init__(self, planner, group=None, solo=False):
         self.pl = planner
         self.group = group
+        self.collectives = 0
+        if solo:                              # whole grid on one GPU: same driver, no process group
+            self.rank, self.world = 0, 1
+            return
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         g = planner.grid
         assert shard_rows(g.Y, self.world, self.rank) == (g.row_begin, g.row_end), \
             "planner rows do not match this rank's shard"
-        self.collectives = 0
 
     # ------------------------------------------------------------------ communication
     def exchange_halos(self, v):
@@ -69,27 +72,69 @@ class ShardedValueIteration(object):
             self.collectives += 1
 
     # ------------------------------------------------------------------ value iteration
+    def _buffers(self, chunk):
+        """Persistent ping-pong value buffers + residual ring (so a captured CUDA graph stays valid)."""
+        st = getattr(self, "_st", None)
+        if st is None or st["chunk"] != chunk:
+            pl = self.pl
+            st = {"chunk": chunk, "bufs": [pl.grid.empty(), pl.grid.empty()],
+                  "ring": pl.new_residuals(chunk + 1), "graphs": {}}
+            self._st = st
+        return st
+
+    def _enqueue_chunk(self, st, n, first, kind0, pol_t, gamma, threshold):
+        """n sweeps: sweep j reads bufs[j % 2], writes bufs[(j+1) % 2], residual -> ring[j+1],
+        gated on ring[j] (the globally reduced residual of the sweep before)."""
+        pl, bufs, ring = self.pl, st["bufs"], st["ring"]
+        for j in range(n):
+            head = first and j == 0
+            self.exchange_halos(bufs[j % 2])
+            pl.sweep(bufs[j % 2], bufs[(j + 1) % 2], kind0 if head else _cabi.GU_POLICY_GREEDY,
+                     pol_t if head else None, gamma, ring[j + 1:j + 2], None if head else ring[j:j + 1], threshold)
+            self.allreduce_max(ring[j + 1:j + 2])
+
     def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                        discount_factor=1.0, chunk=8):
-        """dynamic_programming.py:8-28 on the sharded grid.
-        Returns (V_padded_shard, tie_masks_padded_shard, sweeps, last_delta)."""
+                        discount_factor=1.0, chunk=8, use_graph=True):
+        """dynamic_programming.py:8-28 on the (sharded) grid.
+        Returns (V_padded_shard, tie_masks_padded_shard, sweeps, last_delta).
+
+        Sweeps are enqueued `chunk` at a time with no host round trip inside a chunk; after the
+        first (eager) chunk the steady-state chunk -- ring rotation, halo exchanges, gated
+        fused-greedy sweeps -- is captured once as a CUDA graph and replayed (single-GPU driver)."""
         pl = self.pl
+        # NCCL point-to-point ops inside a captured graph hung on the 2-GPU box (round 1); the
+        # sharded path stays eager until the halo exchange moves to peer-memory stores.
+        use_graph = use_graph and self.world == 1
+        chunk = max(2, int(chunk) + (int(chunk) & 1))          # even, so every chunk starts on bufs[0]
         kind0, pol_t = pl.stage_policy(policy)
         thr = pl.np_dtype.type(threshold)
-        bufs = [pl.stage_value(value_function), pl.grid.empty()]
-        res = pl.new_residuals(max(max_steps, 1))
+        st = self._buffers(chunk)
+        bufs, ring = st["bufs"], st["ring"]
+        bufs[0].copy_(pl.stage_value(value_function))
+        ring.fill_(float("-inf"))
         k, sweeps, last = 0, 0, float("nan")
         converged = False
         while k < max_steps and not converged:
             n = min(chunk, max_steps - k)
-            for _ in range(n):
-                self.exchange_halos(bufs[k % 2])
-                pl.sweep(bufs[k % 2], bufs[(k + 1) % 2], kind0 if k == 0 else _cabi.GU_POLICY_GREEDY,
-                         pol_t if k == 0 else None, discount_factor, res[k:k + 1],
-                         res[k - 1:k] if k > 0 else None, threshold)
-                self.allreduce_max(res[k:k + 1])
-                k += 1
-            r = res[k - n:k].cpu().numpy()
+            first = k == 0
+            key = (float(discount_factor), float(threshold))
+            if first or n < chunk or not use_graph or st["graphs"].get(key) is False:
+                if not first:
+                    ring[0:1].copy_(ring[chunk:chunk + 1])
+                    ring[1:].fill_(float("-inf"))
+                self._enqueue_chunk(st, n, first, kind0, pol_t, discount_factor, threshold)
+            else:
+                graph = st["graphs"].get(key)
+                if graph is None:
+                    graph = self._capture(st, chunk, key, discount_factor, threshold)
+                if graph is False:
+                    continue                                  # capture failed: redo this chunk eagerly
+                graph.replay()
+                pl.launches += chunk
+                if self.world > 1:
+                    self.collectives += 2 * chunk
+            k += n
+            r = ring[1:n + 1].cpu().numpy()
             hit = np.flatnonzero(r < thr)
             if hit.size:
                 sweeps = k - n + int(hit[0]) + 1
@@ -101,6 +146,22 @@ class ShardedValueIteration(object):
         self.exchange_halos(v)               # greedy needs the neighbours' rows of the final V
         tie = pl.greedy(v, discount_factor)
         return v, tie, sweeps, last
+
+    def _capture(self, st, chunk, key, gamma, threshold):
+        ring = st["ring"]
+        try:
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            launches, colls = self.pl.launches, self.collectives
+            with torch.cuda.graph(graph):
+                ring[0:1].copy_(ring[chunk:chunk + 1])
+                ring[1:].fill_(float("-inf"))
+                self._enqueue_chunk(st, chunk, False, None, None, gamma, threshold)
+            self.pl.launches, self.collectives = launches, colls     # capture launched nothing
+            st["graphs"][key] = graph
+        except Exception:                                            # noqa: BLE001 - fall back to eager chunks
+            st["graphs"][key] = False
+        return st["graphs"][key]
 
     def solve_host(self, v0_host, v_out_host, tie_out_host, policy="uniform", **kw):
         """End-to-end solve with HOST buffers (pinned torch tensors holding this rank's owned

@@ -97,7 +97,7 @@ def _worker(rank, world, port, X, Y, chunk, out_dir):
         r0, r1 = shard_rows(Y, world, rank)
         pl = OraclePlanner(wall, goal, lava, X, Y, r0, r1)
         svi = ShardedValueIteration(pl)
-        v, tie, sweeps, last = svi.value_iteration("uniform", None, 1e-6, 1000, 0.9, chunk=chunk)
+        v, tie, sweeps, last = svi.value_iteration("uniform", None, 1e-6, 1000, 0.9, chunk=chunk, use_graph=False)
         V = svi.gather_dense(v).numpy()
         M = svi.gather_dense(tie).numpy()
         if rank == 0:
@@ -106,7 +106,7 @@ def _worker(rank, world, port, X, Y, chunk, out_dir):
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world,chunk", [(2, 8), (3, 5)])
+@pytest.mark.parametrize("world,chunk", [(2, 8), (3, 6)])
 def test_sharded_value_iteration_matches_whole_grid(tmp_path, world, chunk):
     X, Y = 24, 30
     mp.spawn(_worker, args=(world, _free_port(), X, Y, chunk, str(tmp_path)), nprocs=world, join=True)
