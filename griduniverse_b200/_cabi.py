@@ -18,7 +18,7 @@ GU_FLAG_ACCUMULATE = 4
 GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
 
 EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
-           "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_vi_small_f64",
+           "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_vi_small_f64",
            "gu_vi_small_max_cells", "gu_version", "gu_arch", "gu_error_string")
 
 
@@ -34,6 +34,17 @@ class GuGrid(ctypes.Structure):
     _fields_ = [("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("row_begin", ctypes.c_int32),
                 ("row_end", ctypes.c_int32), ("pitch", ctypes.c_int32), ("pitch_words", ctypes.c_int32),
                 ("wall", c_ptr), ("goal", c_ptr), ("lava", c_ptr), ("info", c_ptr)]
+
+
+GU_MAX_PEERS = 16
+
+
+class GuPeerLinks(ctypes.Structure):
+    """struct gu_peer_links (include/gu_b200.h)."""
+    _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("slot", ctypes.c_int32),
+                ("n_slots", ctypes.c_int32), ("up_ghost", c_ptr), ("down_ghost", c_ptr),
+                ("res_tables", c_ptr * GU_MAX_PEERS), ("done_counter", c_ptr), ("error_flag", c_ptr),
+                ("threshold", ctypes.c_double)]
 
 
 class GuError(RuntimeError):
@@ -78,6 +89,9 @@ def lib():
         "gu_sweep_f64": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f64, p, p, f64, p]),
         "gu_sweep_f32": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f32, p, p, f32, p]),
         "gu_pack_info": (ctypes.c_int, [gp, p, p]),
+        "gu_sweep_peer_f32": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f32, p, ctypes.POINTER(GuPeerLinks), p]),
+        "gu_sweep_peer_f64": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f64, p, ctypes.POINTER(GuPeerLinks), p]),
+        "gu_peer_wait": (ctypes.c_int, [ctypes.POINTER(GuPeerLinks), ctypes.c_int, p]),
         "gu_greedy_f64": (ctypes.c_int, [gp, p, p, f64, p]),
         "gu_greedy_f32": (ctypes.c_int, [gp, p, p, f32, p]),
         "gu_vi_small_f64": (ctypes.c_int, [gp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),

@@ -162,11 +162,62 @@ __device__ __forceinline__ bool round_needs_slow(double worst) { return !(worst 
 __device__ __forceinline__ float round_worst_init(float) { return CUDART_INF_F; }
 __device__ __forceinline__ double round_worst_init(double) { return 0.0; }
 
-template <typename T, int KIND, bool WRITE_TIE, int NV>
+// ---- NVLink peer-memory links of a row shard (fused halo exchange + residual all-reduce) --------
+// With PEER the sweep kernel replaces both collectives of the row-sharded value iteration:
+//  * the blocks that own the shard's first / last row also store their output vectors straight
+//    into the ghost row of the neighbour's v_out (peer memory over NVLink);
+//  * the last block to finish publishes the shard's residual into slot `slot` of every rank's
+//    residual table (release, system scope); the next sweep starts by waiting until all `world`
+//    entries of the previous slot have arrived in its local table -- their max is the gate.
+// A sweep gated off after convergence still publishes (the gate value), so waits always complete.
+template <typename T>
+struct PeerArgs {
+  int rank, world, slot;
+  T* up_ghost;                 // neighbour above: bottom ghost row of its v_out, or nullptr
+  T* down_ghost;               // neighbour below: top ghost row of its v_out, or nullptr
+  T* tables[GU_MAX_PEERS];     // rank r's residual table T[slots][world]; tables[rank] is local
+  int* done;                   // local block counter, zero between launches
+  int* err;                    // local error flag (wait timed out)
+  T thr;
+};
+
+constexpr long long kPeerTimeoutCycles = 6000000000ll;   // ~3 s: give up instead of hanging the GPU
+
+template <typename T>
+__device__ __forceinline__ void peer_publish(const PeerArgs<T>& p, T val) {
+  __threadfence_system();
+  for (int r = 0; r < p.world; ++r)
+    *reinterpret_cast<volatile T*>(p.tables[r] + static_cast<size_t>(p.slot) * p.world + p.rank) = val;
+  __threadfence_system();
+}
+
+// max over all ranks of slot `slot` of the local table, spinning until every entry has arrived
+template <typename T>
+__device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot) {
+  const volatile T* tab = p.tables[p.rank] + static_cast<size_t>(slot) * p.world;
+  T m = Num<T>::neg_inf();
+  const long long t0 = clock64();
+  for (int r = 0; r < p.world; ++r) {
+    T v = tab[r];
+    while (v != v) {                              // NaN = not written yet
+      if (clock64() - t0 > kPeerTimeoutCycles) { *p.err = 1; v = -Num<T>::neg_inf(); break; }
+      v = tab[r];
+    }
+    m = v > m ? v : m;
+  }
+  __threadfence_system();
+  return m;
+}
+
+template <typename T>
+__global__ void peer_wait_kernel(PeerArgs<T> p) { (void)peer_wait_slot(p, p.slot); }
+
+template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false>
 __global__ void __launch_bounds__(kTiledWarps * 32)
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
-                   T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block) {
+                   T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block,
+                   PeerArgs<T> peer = PeerArgs<T>()) {
   using N = Num<T>;
   using V = typename Vec<T>::type;
   constexpr int W = Vec<T>::W;
@@ -175,7 +226,17 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   constexpr bool TIES = (KIND == GU_POLICY_GREEDY) || WRITE_TIE;
   __shared__ T scratch[kTiledWarps];
   __shared__ __align__(16) Luts<T> luts;
-  if (gate != nullptr && *gate < gate_thr) return;
+  if (!PEER) {
+    if (gate != nullptr && *gate < gate_thr) return;
+  } else if (peer.slot > 0) {
+    __shared__ T gate_sh;
+    if (threadIdx.x == 0) gate_sh = peer_wait_slot(peer, peer.slot - 1);
+    __syncthreads();
+    if (gate_sh < peer.thr) {                 // converged earlier: pass the verdict on, keep V
+      if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) peer_publish(peer, gate_sh);
+      return;
+    }
+  }
   init_luts(luts);
   __syncthreads();
 
@@ -357,6 +418,16 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(vout + o + k * W) = pack(out + k * W);
+            if (PEER) {
+              if (ry == 0 && peer.up_ghost != nullptr) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(peer.up_ghost + x0 + k * W) = pack(out + k * W);
+              }
+              if (ry == rows - 1 && peer.down_ghost != nullptr) {
+#pragma unroll
+                for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(peer.down_ghost + x0 + k * W) = pack(out + k * W);
+              }
+            }
           }
         }
       }
@@ -365,12 +436,23 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   if (!WRITE_TIE) {
     dmax = warp_max(dmax);
     if (lane == 0) scratch[threadIdx.x >> 5] = dmax;
+    if (PEER) __threadfence_system();          // this thread's ghost-row stores are out before the block reports
     __syncthreads();
     if (threadIdx.x == 0 && residual != nullptr) {
       T m = scratch[0];
 #pragma unroll
       for (int k = 1; k < kTiledWarps; ++k) m = scratch[k] > m ? scratch[k] : m;
       atomic_max_signed(residual, m);
+      if (PEER) {
+        __threadfence();
+        const int nblocks = gridDim.x * gridDim.y;
+        if (atomicAdd(peer.done, 1) == nblocks - 1) {     // last block of the sweep
+          __threadfence();
+          const T fin = *reinterpret_cast<volatile T*>(residual);
+          *peer.done = 0;
+          peer_publish(peer, fin);
+        }
+      }
     }
   }
 }
@@ -429,6 +511,53 @@ template <typename T> struct TiledNV;
 template <> struct TiledNV<float> { static constexpr int value = GU_TILED_NV_F32; };
 template <> struct TiledNV<double> { static constexpr int value = GU_TILED_NV_F64; };
 
+template <typename T>
+static int make_peer_args(const gu_peer_links* pl, PeerArgs<T>* out) {
+  if (!pl || !pl->done_counter || !pl->error_flag) return GU_ERR_NULL;
+  if (pl->world < 1 || pl->world > GU_MAX_PEERS || pl->rank < 0 || pl->rank >= pl->world || pl->slot < 0 ||
+      pl->slot >= pl->n_slots)
+    return GU_ERR_SHAPE;
+  out->rank = pl->rank; out->world = pl->world; out->slot = pl->slot;
+  out->up_ghost = static_cast<T*>(pl->up_ghost);
+  out->down_ghost = static_cast<T*>(pl->down_ghost);
+  for (int r = 0; r < GU_MAX_PEERS; ++r) out->tables[r] = r < pl->world ? static_cast<T*>(pl->res_tables[r]) : nullptr;
+  for (int r = 0; r < pl->world; ++r)
+    if (!out->tables[r]) return GU_ERR_NULL;
+  out->done = pl->done_counter; out->err = pl->error_flag;
+  out->thr = static_cast<T>(pl->threshold);
+  return GU_OK;
+}
+
+template <typename T>
+static int launch_tiled_peer(const gu_grid* g, const T* vin, T* vout, int kind, const void* policy, T gamma,
+                             T* residual, const gu_peer_links* pl, cudaStream_t st) {
+  PeerArgs<T> pa;
+  int rc = make_peer_args(pl, &pa);
+  if (rc) return rc;
+  if (!residual) return GU_ERR_NULL;
+  constexpr int NV = TiledNV<T>::value;
+  constexpr int CPT = Vec<T>::W * NV;
+  const int rows = g->row_end - g->row_begin;
+  const int cols_per_block = kTiledWarps * 32 * CPT;
+  int rpb = GU_TILED_ROWS_PER_BLOCK;
+  dim3 grid((g->X + cols_per_block - 1) / cols_per_block, (rows + rpb - 1) / rpb);
+  if (grid.y > 65535u) return GU_ERR_SHAPE;
+  const GridView v = tview(g);
+#define GU_LAUNCH_PEER(KIND)                                                                                    \
+  sweep_tiled_kernel<T, KIND, false, NV, true><<<grid, kTiledWarps * 32, 0, st>>>(                              \
+      v, g->info, vin, vout, nullptr, policy, gamma, residual, nullptr, T(0), rpb, pa)
+  switch (kind) {
+    case GU_POLICY_PROBS: GU_LAUNCH_PEER(GU_POLICY_PROBS); break;
+    case GU_POLICY_MASK: GU_LAUNCH_PEER(GU_POLICY_MASK); break;
+    case GU_POLICY_UNIFORM: GU_LAUNCH_PEER(GU_POLICY_UNIFORM); break;
+    case GU_POLICY_GREEDY: GU_LAUNCH_PEER(GU_POLICY_GREEDY); break;
+    default: return GU_ERR_MODE;
+  }
+#undef GU_LAUNCH_PEER
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
 template <typename T, bool WRITE_TIE>
 static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, int kind, const void* policy,
                         T gamma, T* residual, const T* gate, T gate_thr, cudaStream_t st) {
@@ -483,6 +612,42 @@ int greedy_tiled_f64(const gu_grid* g, const double* v, uint8_t* tie, double gam
 }  // namespace gu
 
 using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_sweep_peer_f32(
+    const gu_grid* g, const float* v_in, float* v_out, int policy_kind, const void* policy, float gamma,
+    float* residual, const gu_peer_links* peer, void* stream) {
+  if (!g || !v_in || !v_out) return GU_ERR_NULL;
+  if (!tiled_ok(g, sizeof(float), v_in, v_out)) return GU_ERR_UNSUPPORTED;
+  return launch_tiled_peer<float>(g, v_in, v_out, policy_kind, policy, gamma, residual, peer,
+                                  static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_sweep_peer_f64(
+    const gu_grid* g, const double* v_in, double* v_out, int policy_kind, const void* policy, double gamma,
+    double* residual, const gu_peer_links* peer, void* stream) {
+  if (!g || !v_in || !v_out) return GU_ERR_NULL;
+  if (!tiled_ok(g, sizeof(double), v_in, v_out)) return GU_ERR_UNSUPPORTED;
+  return launch_tiled_peer<double>(g, v_in, v_out, policy_kind, policy, gamma, residual, peer,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_peer_wait(const gu_peer_links* peer, int is_f64,
+                                                                     void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (is_f64) {
+    PeerArgs<double> pa;
+    int rc = make_peer_args(peer, &pa);
+    if (rc) return rc;
+    peer_wait_kernel<double><<<1, 1, 0, st>>>(pa);
+  } else {
+    PeerArgs<float> pa;
+    int rc = make_peer_args(peer, &pa);
+    if (rc) return rc;
+    peer_wait_kernel<float><<<1, 1, 0, st>>>(pa);
+  }
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int gu_pack_info(const gu_grid* g, uint8_t* info, void* stream) {
   if (!g || !g->wall || !g->goal || !g->lava || !info) return GU_ERR_NULL;

@@ -190,3 +190,111 @@ class ShardedValueIteration(object):
         outs = [torch.empty_like(buf) for _ in sizes]
         dist.all_gather(outs, buf, group=self.group)
         return torch.cat([o[:s] for o, s in zip(outs, sizes)])
+
+
+class PeerValueIteration(ShardedValueIteration):
+    """Row-sharded value iteration with the collectives fused into the sweep kernel.
+
+    The ping-pong value buffers and the residual tables live in symmetric (peer-mapped) memory
+    (torch.distributed._symmetric_memory).  Each sweep kernel stores its first / last row straight
+    into the neighbours' ghost rows over NVLink, publishes the shard's residual to every rank's
+    table and the next sweep waits for all ranks' entries before it starts (gu_sweep_peer_*,
+    include/gu_b200.h) -- no NCCL call inside the sweep loop.  NCCL is used once per solve for the
+    ghost rows of the initial value function and for two host barriers.
+    Results are bit-identical to the single-GPU and to the NCCL-driven runs."""
+
+    def __init__(self, planner, group=None, max_slots=1024):
+        ShardedValueIteration.__init__(self, planner, group)
+        import torch.distributed._symmetric_memory as symm_mem
+        pl, g = planner, planner.grid
+        self._grp = dist.group.WORLD if group is None else group
+        dev = pl.device
+        all_rows = [shard_rows(g.Y, self.world, r) for r in range(self.world)]
+        self._rows_of = [b - a for a, b in all_rows]
+        max_rows = max(self._rows_of)
+        self.max_slots = int(max_slots)
+        # symmetric allocations must have the same size on every rank
+        self._vsym = symm_mem.empty((2, max_rows + 2, g.pitch), dtype=pl.dtype, device=dev)
+        self._tsym = symm_mem.empty((self.max_slots, self.world), dtype=pl.dtype, device=dev)
+        self._vh = symm_mem.rendezvous(self._vsym, self._grp)
+        self._th = symm_mem.rendezvous(self._tsym, self._grp)
+        self._vsym.zero_()
+        self._bufs = [self._vsym[b, :g.rows + 2] for b in (0, 1)]
+        self._local_res = pl.new_residuals(self.max_slots)
+        self._done = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._err = torch.zeros(1, dtype=torch.int32, device=dev)
+        item = self._vsym.element_size()
+        plane = (max_rows + 2) * g.pitch * item
+        self._ghost = []                                   # per output buffer b: (up_ghost, down_ghost)
+        for b in (0, 1):
+            up = down = None
+            if self.rank > 0:                               # bottom ghost row of the shard above
+                up = self._vh.buffer_ptrs[self.rank - 1] + b * plane + (self._rows_of[self.rank - 1] + 1) * g.pitch * item
+            if self.rank < self.world - 1:                  # top ghost row of the shard below
+                down = self._vh.buffer_ptrs[self.rank + 1] + b * plane
+            self._ghost.append((up, down))
+        self._links = _cabi.GuPeerLinks()
+        self._links.rank, self._links.world, self._links.n_slots = self.rank, self.world, self.max_slots
+        for r in range(self.world):
+            self._links.res_tables[r] = self._th.buffer_ptrs[r]
+        self._links.done_counter = self._done.data_ptr()
+        self._links.error_flag = self._err.data_ptr()
+        self._f64 = pl.np_dtype == np.dtype(np.float64)
+        self._sweep_fn = pl._lib.gu_sweep_peer_f64 if self._f64 else pl._lib.gu_sweep_peer_f32
+
+    def _sweep_peer(self, k, kind, pol_t, gamma, threshold):
+        import ctypes
+        pl = self.pl
+        out = (k + 1) % 2
+        up, down = self._ghost[out]
+        L = self._links
+        L.slot, L.threshold = k, float(threshold)
+        L.up_ghost, L.down_ghost = up, down
+        rc = self._sweep_fn(pl.grid.ref(), _cabi.ptr(self._bufs[k % 2]), _cabi.ptr(self._bufs[out]), kind,
+                            _cabi.ptr(pol_t), float(gamma), _cabi.ptr(self._local_res[k:k + 1]),
+                            ctypes.byref(L), _cabi.stream_ptr())
+        _cabi.check("gu_sweep_peer", rc)
+        pl.launches += 1
+
+    def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
+                        discount_factor=1.0, chunk=16, use_graph=False):
+        import ctypes
+        pl = self.pl
+        assert max_steps <= self.max_slots, "raise max_slots"
+        kind0, pol_t = pl.stage_policy(policy)
+        thr = pl.np_dtype.type(threshold)
+        # nobody may still be publishing into the tables of the previous solve when they are reset,
+        # and every table must be reset before the first sweep of this solve publishes
+        dist.barrier(group=self.group)
+        self._tsym.fill_(float("nan"))
+        self._local_res.fill_(float("-inf"))
+        self._done.zero_()
+        self._err.zero_()
+        self._bufs[0].copy_(pl.stage_value(value_function))
+        self.exchange_halos(self._bufs[0])                 # ghost rows of V0 (NCCL, once per solve)
+        torch.cuda.synchronize()
+        dist.barrier(group=self.group)
+        k, sweeps, last = 0, 0, float("nan")
+        converged = False
+        while k < max_steps and not converged:
+            n = min(chunk, max_steps - k)
+            for _ in range(n):
+                self._sweep_peer(k, kind0 if k == 0 else _cabi.GU_POLICY_GREEDY, pol_t if k == 0 else None,
+                                 discount_factor, threshold)
+                k += 1
+            self._links.slot = k - 1                       # all ranks' entries of the chunk's last slot
+            _cabi.check("gu_peer_wait", pl._lib.gu_peer_wait(ctypes.byref(self._links), int(self._f64),
+                                                             _cabi.stream_ptr()))
+            r = self._tsym[k - n:k].max(dim=1).values.cpu().numpy()
+            if int(self._err.item()):
+                raise RuntimeError("peer wait timed out: a rank of the sharded value iteration stalled")
+            hit = np.flatnonzero(r < thr)
+            if hit.size:
+                sweeps = k - n + int(hit[0]) + 1
+                last = float(r[hit[0]])
+                converged = True
+            else:
+                sweeps, last = k, float(r[-1])
+        v = self._bufs[sweeps % 2]
+        tie = pl.greedy(v, discount_factor)                # ghost rows of V are current (peer stores)
+        return v, tie, sweeps, last

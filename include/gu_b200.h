@@ -187,6 +187,40 @@ int gu_sweep_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_k
                  const void* policy, float gamma, float* residual, const float* gate,
                  float gate_threshold, void* stream);
 
+/* Row-sharded sweeps fused with their collectives over NVLink peer memory (no NCCL in the
+ * loop).  Each rank passes pointers into its neighbours' and peers' memory (e.g. from
+ * torch.distributed._symmetric_memory):
+ *   up_ghost / down_ghost: the ghost row of the neighbour's v_out that mirrors this shard's
+ *     first / last row (NULL at the grid edge).  The kernel stores those rows there directly.
+ *   res_tables[r]: rank r's residual table T[n_slots][world], NaN-initialised; res_tables[rank]
+ *     is this rank's own.  Sweep number `slot` writes max(v_in - v_out) of the shard to entry
+ *     [slot][rank] of EVERY table when its last block finishes; sweep slot+1 first waits until
+ *     all `world` entries of [slot] have arrived locally and is a no-op (republishing the value)
+ *     if their max is below `threshold` -- the reference's stopping rule
+ *     (dynamic_programming.py:17,22-23) evaluated identically on every rank.
+ *   residual: local T scalar for this sweep, initialised to -inf; done_counter: local int32 = 0.
+ * Needs the tiled layout (info plane, pitch % 32 == 0).  gu_peer_wait blocks the stream until
+ * slot `slot` is complete (use before the host reads the table). */
+#define GU_MAX_PEERS 16
+typedef struct {
+  int32_t rank, world;
+  int32_t slot, n_slots;
+  void* up_ghost;
+  void* down_ghost;
+  void* res_tables[GU_MAX_PEERS];
+  int32_t* done_counter;
+  int32_t* error_flag;
+  double threshold;
+} gu_peer_links;
+
+int gu_sweep_peer_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_kind,
+                      const void* policy, float gamma, float* residual, const gu_peer_links* peer,
+                      void* stream);
+int gu_sweep_peer_f64(const gu_grid* g, const double* v_in, double* v_out, int policy_kind,
+                      const void* policy, double gamma, double* residual, const gu_peer_links* peer,
+                      void* stream);
+int gu_peer_wait(const gu_peer_links* peer, int is_f64, void* stream);
+
 /* greedy_policy_from_value_function (utils.py:55-72) as a tie mask per cell:
  * bit a set <=> rint(q[s,a]*1e8) == rint(max_a q[s,a]*1e8) and s is not terminal,
  * q[s,a] = R[next] + g*v[next].  np.argmax of the expanded row is ctz(mask). */

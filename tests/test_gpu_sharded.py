@@ -20,7 +20,7 @@ def _free_port():
     return port
 
 
-def _worker(rank, world, port, X, Y, dtype_name, out_dir):
+def _worker(rank, world, port, X, Y, dtype_name, out_dir, mode="nccl"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     torch.cuda.set_device(rank)
@@ -28,12 +28,15 @@ def _worker(rank, world, port, X, Y, dtype_name, out_dir):
     try:
         from griduniverse_b200 import synth
         from griduniverse_b200.planner import Planner
-        from griduniverse_b200.sharded import ShardedValueIteration, shard_rows
+        from griduniverse_b200.sharded import PeerValueIteration, ShardedValueIteration, shard_rows
         dt = np.dtype(dtype_name)
         r0, r1 = shard_rows(Y, world, rank)
         grid = synth.maze_plan_grid(X, Y, seed=3, dtype=dt, device="cuda:%d" % rank, row_begin=r0, row_end=r1)
-        svi = ShardedValueIteration(Planner(None, dt, "cuda:%d" % rank, grid=grid))
+        cls = PeerValueIteration if mode == "peer" else ShardedValueIteration
+        svi = cls(Planner(None, dt, "cuda:%d" % rank, grid=grid))
         v, tie, sweeps, last = svi.value_iteration("uniform", None, 1e-6, 1000, 0.9, chunk=8)
+        if mode == "peer":                                 # a second solve on the same driver (table reset path)
+            v, tie, sweeps, last = svi.value_iteration("uniform", None, 1e-6, 1000, 0.9, chunk=5)
         V = svi.gather_dense(v)
         M = svi.gather_dense(tie)
         if rank == 0:
@@ -42,14 +45,15 @@ def _worker(rank, world, port, X, Y, dtype_name, out_dir):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("mode", ["nccl", "peer"])
 @pytest.mark.parametrize("dtype_name,shape", [("float64", (160, 96)), ("float32", (1024, 512))])
-def test_sharded_vi_matches_single_gpu(tmp_path, dtype_name, shape):
+def test_sharded_vi_matches_single_gpu(tmp_path, dtype_name, shape, mode):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     from griduniverse_b200 import synth
     from griduniverse_b200.planner import Planner
     X, Y = shape
-    mp.spawn(_worker, args=(2, _free_port(), X, Y, dtype_name, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), X, Y, dtype_name, str(tmp_path), mode), nprocs=2, join=True)
     out = np.load(os.path.join(str(tmp_path), "sharded.npz"))
     dt = np.dtype(dtype_name)
     grid = synth.maze_plan_grid(X, Y, seed=3, dtype=dt, device="cuda:0")
