@@ -167,7 +167,7 @@ def run_ours(args):
     from griduniverse_b200 import synth
     from griduniverse_b200.envs import GridUniverseVecEnv
     from griduniverse_b200.planner import Planner
-    from griduniverse_b200.sharded import ShardedValueIteration, shard_envs, shard_rows
+    from griduniverse_b200.sharded import PeerValueIteration, ShardedValueIteration, shard_envs, shard_rows
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -275,7 +275,13 @@ def run_ours(args):
     r0, r1 = shard_rows(VI_SIZE, world, rank)
     grid = synth.maze_plan_grid(VI_SIZE, VI_SIZE, seed=0, dtype=np.float32, device=dev, row_begin=r0, row_end=r1)
     pl = Planner(None, np.float32, dev, grid=grid)
-    svi = ShardedValueIteration(pl, solo=(world == 1))
+    vi_comm = "none"
+    if world == 1:
+        svi = ShardedValueIteration(pl, solo=True)
+    elif args.vi_comm == "nccl":
+        svi, vi_comm = ShardedValueIteration(pl), "nccl send/recv + all-reduce per sweep"
+    else:
+        svi, vi_comm = PeerValueIteration(pl), "fused in the sweep kernel: NVLink peer-memory halo stores + residual tables"
     vi_meta = {}
 
     def vi_pass():
@@ -349,7 +355,7 @@ def run_ours(args):
                 "solves_timed": k_vi, "scaling": "strong",
                 "config": {"workload": "cfg5: value iteration on a 16384x16384 synthetic maze, gamma 0.9, "
                                        "theta 1e-6, uniform policy0, V0=0",
-                           "parallelism": "row-sharded x%d, halo send/recv + residual MAX all-reduce per sweep" % world,
+                           "parallelism": "row-sharded x%d; halo exchange + residual max: %s" % (world, vi_comm),
                            "l2": "inputs larger than L2 (%.2f GB of V per GPU)" % ((r1 - r0) * VI_SIZE * 4 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": vi_achieved, "peak": peak, "unit": "GB/s",
                              "frac": vi_achieved / peak, "traffic": profiled_traffic("sweep_greedy_f32_cfg5", (r1 - r0) / float(VI_SIZE)),
@@ -406,6 +412,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--vi-comm", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU value iteration: collectives fused over peer memory (default) or NCCL")
     ap.add_argument("--profile", action="store_true", help="short kernel sequence for ncu")
     ap.add_argument("--profile-div", type=int, default=1, help="shrink the profile workloads by this factor")
     args = ap.parse_args()

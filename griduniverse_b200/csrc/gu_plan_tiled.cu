@@ -193,7 +193,7 @@ __device__ __forceinline__ void peer_publish(const PeerArgs<T>& p, T val) {
 
 // max over all ranks of slot `slot` of the local table, spinning until every entry has arrived
 template <typename T>
-__device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot) {
+__device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot, bool acquire = true) {
   const volatile T* tab = p.tables[p.rank] + static_cast<size_t>(slot) * p.world;
   T m = Num<T>::neg_inf();
   const long long t0 = clock64();
@@ -205,7 +205,7 @@ __device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot) {
     }
     m = v > m ? v : m;
   }
-  __threadfence_system();
+  if (acquire) __threadfence_system();   // only readers of peer-written ghost rows need the system fence
   return m;
 }
 
@@ -230,7 +230,10 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     if (gate != nullptr && *gate < gate_thr) return;
   } else if (peer.slot > 0) {
     __shared__ T gate_sh;
-    if (threadIdx.x == 0) gate_sh = peer_wait_slot(peer, peer.slot - 1);
+    // blocks that read a ghost row (first / last block row) acquire at system scope; the others only
+    // need the gate value itself
+    const bool edge_block = blockIdx.y == 0 || blockIdx.y == gridDim.y - 1;
+    if (threadIdx.x == 0) gate_sh = peer_wait_slot(peer, peer.slot - 1, edge_block);
     __syncthreads();
     if (gate_sh < peer.thr) {                 // converged earlier: pass the verdict on, keep V
       if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) peer_publish(peer, gate_sh);
@@ -436,7 +439,8 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   if (!WRITE_TIE) {
     dmax = warp_max(dmax);
     if (lane == 0) scratch[threadIdx.x >> 5] = dmax;
-    if (PEER) __threadfence_system();          // this thread's ghost-row stores are out before the block reports
+    // ghost-row stores of the first / last block row are out (system scope) before the block reports
+    if (PEER && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0 && residual != nullptr) {
       T m = scratch[0];
