@@ -285,7 +285,7 @@ def run_ours(args):
     vi_meta = {}
 
     def vi_pass():
-        v, tie, sweeps, last = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=8)
+        v, tie, sweeps, last = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
         vi_meta["sweeps"], vi_meta["last"] = sweeps, last
 
     vi_pass()                                          # warm-up solve (also fixes the sweep count)
@@ -314,9 +314,10 @@ def run_ours(args):
 
     def vi_e2e_pass():
         s, last, h2d, d2h = svi.solve_host(v0_h, v_h, tie_h, "uniform", threshold=VI_THETA, max_steps=1000,
-                                           discount_factor=VI_GAMMA, chunk=8)
+                                           discount_factor=VI_GAMMA, chunk=16)
         io["h2d"], io["d2h"], io["sweeps"] = h2d, d2h, s
 
+    vi_e2e_pass()
     t_vi_e2e = timed(vi_e2e_pass, 1)
     vi_e2e_value = io["sweeps"] * cells / t_vi_e2e
     clocks = sampler.stop() if sampler else None

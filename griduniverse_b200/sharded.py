@@ -241,6 +241,7 @@ class PeerValueIteration(ShardedValueIteration):
         self._links.error_flag = self._err.data_ptr()
         self._f64 = pl.np_dtype == np.dtype(np.float64)
         self._sweep_fn = pl._lib.gu_sweep_peer_f64 if self._f64 else pl._lib.gu_sweep_peer_f32
+        self.exchange_halos(self._bufs[0])     # sets up NCCL's point-to-point channels outside any timed solve
 
     def _sweep_peer(self, k, kind, pol_t, gamma, threshold):
         import ctypes
@@ -265,15 +266,18 @@ class PeerValueIteration(ShardedValueIteration):
         thr = pl.np_dtype.type(threshold)
         # nobody may still be publishing into the tables of the previous solve when they are reset,
         # and every table must be reset before the first sweep of this solve publishes
-        dist.barrier(group=self.group)
+        # (symmetric-memory barriers: signal pads over NVLink, stream-ordered)
+        self._th.barrier()
         self._tsym.fill_(float("nan"))
         self._local_res.fill_(float("-inf"))
         self._done.zero_()
         self._err.zero_()
-        self._bufs[0].copy_(pl.stage_value(value_function))
-        self.exchange_halos(self._bufs[0])                 # ghost rows of V0 (NCCL, once per solve)
-        torch.cuda.synchronize()
-        dist.barrier(group=self.group)
+        if value_function is None:
+            self._bufs[0].zero_()                          # V0 = 0 everywhere, ghost rows included
+        else:
+            self._bufs[0].copy_(pl.stage_value(value_function))
+            self.exchange_halos(self._bufs[0])             # ghost rows of V0 (NCCL, once per solve)
+        self._th.barrier()
         k, sweeps, last = 0, 0, float("nan")
         converged = False
         while k < max_steps and not converged:
