@@ -83,6 +83,9 @@ __device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], flo
   for (int a = 0; a < 4; ++a) c = __fmaf_rn(w[a], 4.0f, c);
   const float p = *reinterpret_cast<const float*>(reinterpret_cast<const char*>(&l.inv_cnt[0]) +
                                                   (__float_as_uint(c) & 0x1cu));
+  // non-tied actions add (0 * (p*g)) = +-0, which leaves the non-zero running sum bit-identical.
+  // (Folding w into a fused multiply-add, acc = fma(w, p*g, acc), is also exact and saves four
+  // instructions per cell, but measured 2 % slower on B200: the dependent FFMA chain is longer.)
   float acc = rs;
 #pragma unroll
   for (int a = 0; a < 4; ++a) acc = __fadd_rn(acc, __fmul_rn(w[a], __fmul_rn(p, ga[a])));
