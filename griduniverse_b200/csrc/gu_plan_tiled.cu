@@ -15,6 +15,8 @@
 //
 // Per-cell static data comes from the derived `info` plane (gu_pack_info): one bit per action
 // "a is blocked" (grid edge | wall at the target | s terminal) plus the goal and lava bits.
+#include <cstdlib>
+
 #include "gu_cell.cuh"
 
 namespace gu {
@@ -520,6 +522,37 @@ template <typename T> struct TiledNV;
 template <> struct TiledNV<float> { static constexpr int value = GU_TILED_NV_F32; };
 template <> struct TiledNV<double> { static constexpr int value = GU_TILED_NV_F64; };
 
+// Rows per block: the default amortises the two halo rows of a block over 48 rows.  When a shard is
+// small enough that the grid is only a few waves of resident blocks, pick the row-block count that
+// fills whole waves instead (e.g. 2048 rows x 16 column blocks on 148 SMs x 4 blocks: 56 rows per
+// block = exactly one wave instead of 1.16).
+template <typename K>
+static int choose_rows_per_block(K kernel, int rows, int blocks_x) {
+  const int def = GU_TILED_ROWS_PER_BLOCK;
+  static const char* fixed = getenv("GU_TILED_FIXED_RPB");   // developer switch for A/B timing
+  if (fixed) return def;
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  int per_sm = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kTiledWarps * 32, 0) != cudaSuccess || per_sm <= 0)
+    return def;
+  const long long slots = static_cast<long long>(sms) * per_sm;
+  const long long blocks_def = static_cast<long long>(blocks_x) * ((rows + def - 1) / def);
+  if (blocks_def >= 6 * slots) return def;            // many waves: quantisation is negligible
+  for (int w = 1; w <= 8; ++w) {
+    const long long nby = (w * slots) / blocks_x;
+    if (nby <= 0) continue;
+    const int rpb = static_cast<int>((rows + nby - 1) / nby);
+    if (rpb >= 16 && rpb <= 72) return rpb;
+  }
+  return def;
+}
+
 template <typename T>
 static int make_peer_args(const gu_peer_links* pl, PeerArgs<T>* out) {
   if (!pl || !pl->done_counter || !pl->error_flag) return GU_ERR_NULL;
@@ -548,8 +581,9 @@ static int launch_tiled_peer(const gu_grid* g, const T* vin, T* vout, int kind, 
   constexpr int CPT = Vec<T>::W * NV;
   const int rows = g->row_end - g->row_begin;
   const int cols_per_block = kTiledWarps * 32 * CPT;
-  int rpb = GU_TILED_ROWS_PER_BLOCK;
-  dim3 grid((g->X + cols_per_block - 1) / cols_per_block, (rows + rpb - 1) / rpb);
+  const int bx = (g->X + cols_per_block - 1) / cols_per_block;
+  const int rpb = choose_rows_per_block(sweep_tiled_kernel<T, GU_POLICY_GREEDY, false, NV, true>, rows, bx);
+  dim3 grid(bx, (rows + rpb - 1) / rpb);
   if (grid.y > 65535u) return GU_ERR_SHAPE;
   const GridView v = tview(g);
 #define GU_LAUNCH_PEER(KIND)                                                                                    \
@@ -574,8 +608,9 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
   constexpr int CPT = Vec<T>::W * NV;
   const int rows = g->row_end - g->row_begin;
   const int cols_per_block = kTiledWarps * 32 * CPT;
-  int rpb = GU_TILED_ROWS_PER_BLOCK;               // rows per block (halo re-read: 2 rows per block)
-  dim3 grid((g->X + cols_per_block - 1) / cols_per_block, (rows + rpb - 1) / rpb);
+  const int bx = (g->X + cols_per_block - 1) / cols_per_block;
+  const int rpb = choose_rows_per_block(sweep_tiled_kernel<T, GU_POLICY_GREEDY, WRITE_TIE, NV, false>, rows, bx);
+  dim3 grid(bx, (rows + rpb - 1) / rpb);
   if (grid.y > 65535u) return GU_ERR_SHAPE;
   const GridView v = tview(g);
   const uint8_t* info = g->info;

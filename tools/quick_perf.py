@@ -17,18 +17,19 @@ def timeit(fn, n=10, warm=3):
 
 what = sys.argv[1] if len(sys.argv) > 1 else "all"
 size = int(os.environ.get("SIZE", "16384"))
+rows_n = int(os.environ.get("ROWS", str(size)))
 if what in ("all", "sweep"):
     for dt, bpc in ((np.float32, 8.375), (np.float64, 16.375)):
         if os.environ.get('ONLY') == 'f32' and dt != np.float32: continue
         if os.environ.get('ONLY') == 'f64' and dt != np.float64: continue
-        grid = synth.maze_plan_grid(size, size, seed=0, dtype=dt)
+        grid = synth.maze_plan_grid(size, rows_n, seed=0, dtype=dt)
         pl = Planner(None, dt, "cuda", grid=grid)
         a, b = grid.empty(), grid.empty()
         a.normal_()
         tie = pl.greedy(a, 0.9)
         for kind, name, extra in ((3, "greedy", 0), (2, "uniform", 0), (1, "mask", 1)):
             ms = timeit(lambda: pl.sweep(a, b, kind, tie if kind == 1 else None, 0.9))
-            cells = size * size
+            cells = size * rows_n
             print("%s %-8s %.3f ms  %.3e cells/s  %.0f GB/s alg (%.1f%% of 6455.6)" % (
                 dt.__name__, name, ms, cells / ms * 1e3, (bpc + extra) * cells / ms / 1e6, (bpc + extra) * cells / ms / 1e6 / 64.556))
         ms = timeit(lambda: pl.greedy(a, 0.9))
