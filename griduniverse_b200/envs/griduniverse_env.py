@@ -7,7 +7,8 @@ single call costs one launch + one device->host read.  There is no CPU transitio
 this class: without a CUDA device `step` raises.  Use ``GridUniverseVecEnv`` for throughput.
 
 Not carried over: the pyglet viewer (`render(mode='graphic')`, `render_policy_arrows`) --
-GUI, out of scope.
+GUI, out of scope.  `random_maze=True` works but uses this repo's own
+depth-first maze carver, so a given `random.seed` does not reproduce the reference's maze.
 """
 import random
 import sys
@@ -24,15 +25,13 @@ class GridUniverseEnv(object):
 
     def __init__(self, grid_shape=(4, 4), *, initial_state=0, goal_states=None, lava_states=None, walls=None,
                  custom_world_fp=None, random_maze=False, device="cuda"):
-        # parameter checks: griduniverse_env.py:35-43
-        if goal_states is not None and not isinstance(goal_states, list):
-            raise TypeError("goal_states parameter must be a list of integer indices")
-        if lava_states is not None and not isinstance(lava_states, list):
-            raise TypeError("lava_states parameter must be a list of integer indices")
-        if walls is not None and not isinstance(walls, list):
-            raise TypeError("walls parameter must be a list of integer indices")
-        if not (isinstance(grid_shape, list) or isinstance(grid_shape, tuple)) or len(grid_shape) != 2 \
-                or not isinstance(grid_shape[0], int) or not isinstance(grid_shape[1], int):
+        # parameter checks with the reference's messages and exception types (griduniverse_env.py:35-43)
+        for name, value in (("goal_states", goal_states), ("lava_states", lava_states), ("walls", walls)):
+            if value is not None and not isinstance(value, list):
+                raise TypeError("{} parameter must be a list of integer indices".format(name))
+        shape_ok = isinstance(grid_shape, (list, tuple)) and len(grid_shape) == 2 and \
+            all(isinstance(d, int) for d in grid_shape)
+        if not shape_ok:
             raise TypeError("grid_shape parameter must be tuple/list of two integers")
         self._device = device
         self._vec = None
@@ -55,10 +54,10 @@ class GridUniverseEnv(object):
         if custom_world_fp:
             self._create_custom_world_from_file(custom_world_fp)
         if random_maze:
-            raise NotImplementedError(
-                "random_maze=True relies on the reference's serial maze generator "
-                "(core/envs/maze_generation.py), which is out of scope for the B200 hot path; "
-                "generate the level text elsewhere and pass custom_world_fp / from_text_lines()")
+            # the reference replaces every level argument by a generated maze of the requested shape
+            # (griduniverse_env.py:106-107,318-321); ours comes from an independent generator
+            from ..synth import random_maze_lines
+            self._create_custom_world_from_text(random_maze_lines(self.x_max, self.y_max))
 
     # ------------------------------------------------------------------ level plumbing
     def _install_level(self, level):
@@ -145,21 +144,15 @@ class GridUniverseEnv(object):
         """ASCII render (griduniverse_env.py:195-221); glyph precedence x < G < L < #."""
         if close:
             return
-        if mode == 'human' or mode == 'ansi':
-            new_world = np.full(self.world.size, 'o', dtype='<U1')
-            new_world[self.current_state] = 'x'
-            for t_state in self.goal_states:
-                new_world[t_state] = 'G'
-            for t_state in self.lava_states:
-                new_world[t_state] = 'L'
-            for w_state in self.wall_indices:
-                new_world[w_state] = '#'
+        if mode in ('human', 'ansi'):
+            glyphs = np.full(self.world.size, 'o', dtype='<U1')
+            glyphs[self.current_state] = 'x'
+            glyphs[self.level.goal] = 'G'
+            glyphs[self.level.lava] = 'L'
+            glyphs[self.level.wall] = '#'
+            text = ''.join(''.join(g + ' ' for g in row) + '\n' for row in glyphs.reshape(self.y_max, self.x_max))
             outfile = StringIO() if mode == 'ansi' else sys.stdout
-            for row in np.reshape(new_world, (self.y_max, self.x_max)):
-                for state in row:
-                    outfile.write(state + ' ')
-                outfile.write('\n')
-            outfile.write('\n')
+            outfile.write(text + '\n')
             return outfile
         raise NotImplementedError("render mode %r: the pyglet viewer is out of scope" % (mode,))
 

@@ -148,3 +148,39 @@ def maze_plan_grid(X, Y, seed=0, dtype=np.float32, device="cuda", row_begin=0, r
     _cabi.check("gu_synth_maze", rc)
     g.finish()
     return g
+
+
+# --------------------------------------------------------------------------
+# small random mazes for `GridUniverseEnv(random_maze=True)` (host, one-off)
+# --------------------------------------------------------------------------
+def random_maze_lines(width, height, rng=None):
+    """A perfect maze carved by depth-first search on the cells two apart from a random origin,
+    with one start 'x' and one goal 'G' dropped on two distinct open cells; returned as level
+    text lines.  Same idea as the reference's generator (core/envs/maze_generation.py:41-149:
+    recursive backtracker + random start / goal) but an independent implementation -- the mazes
+    are reproducible from Python's `random` seed, not identical to the reference's."""
+    import random as _random
+    rng = rng or _random
+    wall = [[True] * width for _ in range(height)]
+    ox, oy = rng.randrange(width), rng.randrange(height)
+    wall[oy][ox] = False
+    stack = [(ox, oy)]
+    while stack:
+        x, y = stack[-1]
+        options = [(x + dx, y + dy, x + dx // 2, y + dy // 2) for dx, dy in ((2, 0), (-2, 0), (0, 2), (0, -2))
+                   if 0 <= x + dx < width and 0 <= y + dy < height and wall[y + dy][x + dx]]
+        if not options:
+            stack.pop()
+            continue
+        nx, ny, mx, my = rng.choice(options)
+        wall[my][mx] = False
+        wall[ny][nx] = False
+        stack.append((nx, ny))
+    open_cells = [(x, y) for y in range(height) for x in range(width) if not wall[y][x]]
+    if len(open_cells) < 2:
+        raise ValueError("grid too small for a maze with a start and a goal")
+    (sx, sy), (gx, gy) = rng.sample(open_cells, 2)
+    rows = [['#' if wall[y][x] else 'o' for x in range(width)] for y in range(height)]
+    rows[sy][sx] = 'x'
+    rows[gy][gx] = 'G'
+    return [''.join(r) for r in rows]

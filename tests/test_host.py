@@ -165,3 +165,19 @@ def test_product_fails_loudly_without_cuda():
     env = GridUniverseEnv()
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         env.step(1)
+
+
+def test_random_maze_constructor():
+    import random
+    random.seed(3)
+    env = GridUniverseEnv(grid_shape=(11, 9), random_maze=True)
+    assert (env.x_max, env.y_max, env.world.size) == (11, 9, 99)
+    assert len(env.starting_states) == 1 and len(env.goal_states) == 1 and env.lava_states == []
+    assert env.starting_states[0] != env.goal_states[0] and len(env.wall_indices) > 20
+    lv = env.level
+    # perfect maze: the open cells form a tree (edges = cells - 1) and the goal is reachable
+    open_ = ~lv.wall.reshape(9, 11)
+    edges = (open_[:, 1:] & open_[:, :-1]).sum() + (open_[1:] & open_[:-1]).sum()
+    assert edges == open_.sum() - 1
+    random.seed(3)
+    assert GridUniverseEnv(grid_shape=(11, 9), random_maze=True).level.to_text_lines() == lv.to_text_lines()
