@@ -95,9 +95,10 @@ __device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], flo
   for (int a = 0; a < 4; ++a) acc = __fadd_rn(acc, __fmul_rn(w[a], __fmul_rn(p, ga[a])));
   return acc;
 }
-// f64: compares feed predicated mul / add pairs directly.
+// f64: plain predicated form (the compiler keeps the four compares in predicate registers).
 __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, const double (&ga)[4],
                                               const Luts<double>& l) {
+#ifdef GU_F64_ASM_BACKUP
   double acc;
   const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(&l.inv_cnt[0]));
   asm("{\n\t"
@@ -129,6 +130,16 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
       : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
         "d"(ga[3]), "r"(lut));
   return acc;
+#else
+  const bool t0 = ra[0] == m, t1 = ra[1] == m, t2 = ra[2] == m, t3 = ra[3] == m;
+  const double p = l.inv_cnt[(t0 ? 1 : 0) + (t1 ? 1 : 0) + (t2 ? 1 : 0) + (t3 ? 1 : 0)];
+  double acc = rs;
+  if (t0) acc = __dadd_rn(acc, __dmul_rn(p, ga[0]));
+  if (t1) acc = __dadd_rn(acc, __dmul_rn(p, ga[1]));
+  if (t2) acc = __dadd_rn(acc, __dmul_rn(p, ga[2]));
+  if (t3) acc = __dadd_rn(acc, __dmul_rn(p, ga[3]));
+  return acc;
+#endif
 }
 
 #ifndef GU_TILED_WARPS
@@ -138,6 +149,10 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
 #define GU_TILED_PREFETCH_ROWS 3
 #endif
 constexpr int kTiledWarps = GU_TILED_WARPS;
+
+// max without NaN semantics: one compare + select (fmax(double) costs ~7 instructions on sm_100)
+__device__ __forceinline__ float max_nn(float a, float b) { return fmaxf(a, b); }
+__device__ __forceinline__ double max_nn(double a, double b) { return a > b ? a : b; }
 
 // One row of the sliding window.  v / info / hv / hinfo are loaded one row of compute ahead
 // ("raw" part); convert() derives the discounted values g and the rounded scaled q-values rt
@@ -161,7 +176,7 @@ __device__ __forceinline__ float round_fast(float t, float& worst) {
   return t;
 }
 __device__ __forceinline__ double round_fast(double t, double& worst) {
-  worst = fmax(worst, fabs(t));             // slow path if any |t| >= 2^51
+  worst = max_nn(worst, fabs(t));           // slow path if any |t| >= 2^51
   return __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
 }
 __device__ __forceinline__ bool round_needs_slow(float worst) { return worst < 8388608.0f; }
@@ -387,7 +402,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               ra[2] = (inf & kBlkD) ? rts : dn.rt[c];
               ra[3] = (inf & kBlkL) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
               // terminal rows are all zero (utils.py:70): NaN never compares equal
-              m = N::add(fmax(fmax(ra[0], ra[1]), fmax(ra[2], ra[3])), rp.y);
+              m = N::add(max_nn(max_nn(ra[0], ra[1]), max_nn(ra[2], ra[3])), rp.y);
             }
             if constexpr (WRITE_TIE) {
               const uint32_t mk = (ra[0] == m ? 1u : 0u) | (ra[1] == m ? 2u : 0u) | (ra[2] == m ? 4u : 0u) |
@@ -420,11 +435,11 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
           } else {
             if (full) {
 #pragma unroll
-              for (int c = 0; c < CPT; ++c) dmax = fmax(dmax, N::add(cur.v[c], -out[c]));
+              for (int c = 0; c < CPT; ++c) dmax = max_nn(dmax, N::add(cur.v[c], -out[c]));
             } else {
 #pragma unroll
               for (int c = 0; c < CPT; ++c)
-                if (x0 + c < g.X) dmax = fmax(dmax, N::add(cur.v[c], -out[c]));
+                if (x0 + c < g.X) dmax = max_nn(dmax, N::add(cur.v[c], -out[c]));
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(vout + o + k * W) = pack(out + k * W);
