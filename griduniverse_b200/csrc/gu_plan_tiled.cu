@@ -95,10 +95,10 @@ __device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], flo
   for (int a = 0; a < 4; ++a) acc = __fadd_rn(acc, __fmul_rn(w[a], __fmul_rn(p, ga[a])));
   return acc;
 }
-// f64: plain predicated form (the compiler keeps the four compares in predicate registers).
+// f64: the four compares feed predicated mul / add pairs (PTX).  A/B on B200 at 16384^2:
+// 1.38 ms this way, 1.42 ms with C++ selects, 1.54 ms with 0/1 weight multiplies.
 __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, const double (&ga)[4],
                                               const Luts<double>& l) {
-#ifdef GU_F64_ASM_BACKUP
   double acc;
   const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(&l.inv_cnt[0]));
   asm("{\n\t"
@@ -130,16 +130,6 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
       : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
         "d"(ga[3]), "r"(lut));
   return acc;
-#else
-  const bool t0 = ra[0] == m, t1 = ra[1] == m, t2 = ra[2] == m, t3 = ra[3] == m;
-  const double p = l.inv_cnt[(t0 ? 1 : 0) + (t1 ? 1 : 0) + (t2 ? 1 : 0) + (t3 ? 1 : 0)];
-  double acc = rs;
-  if (t0) acc = __dadd_rn(acc, __dmul_rn(p, ga[0]));
-  if (t1) acc = __dadd_rn(acc, __dmul_rn(p, ga[1]));
-  if (t2) acc = __dadd_rn(acc, __dmul_rn(p, ga[2]));
-  if (t3) acc = __dadd_rn(acc, __dmul_rn(p, ga[3]));
-  return acc;
-#endif
 }
 
 #ifndef GU_TILED_WARPS
