@@ -281,7 +281,16 @@ def run_ours(args):
     elif args.vi_comm == "nccl":
         svi, vi_comm = ShardedValueIteration(pl), "nccl send/recv + all-reduce per sweep"
     else:
-        svi, vi_comm = PeerValueIteration(pl), "fused in the sweep kernel: NVLink peer-memory halo stores + residual tables"
+        vi_comm = "fused in the sweep kernel: NVLink peer-memory halo stores + residual tables"
+        try:
+            svi = PeerValueIteration(pl)
+            ok = torch.ones(1, device=dev)
+        except Exception as e:      # noqa: BLE001 - e.g. no symmetric memory on this box: fall back to NCCL
+            sys.stderr.write("rank %d: peer-memory driver unavailable (%s); using NCCL collectives\n" % (rank, e))
+            svi, ok = None, torch.zeros(1, device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank must take the same path
+        if ok.item() == 0:
+            svi, vi_comm = ShardedValueIteration(pl), "nccl send/recv + all-reduce per sweep (fallback)"
     vi_meta = {}
 
     def vi_pass():
