@@ -1,20 +1,18 @@
 // gu_env_tables.cu -- table-driven rollout kernels (transition tables staged in shared memory).
 //
 // A level is static, so look_step_ahead (core/envs/griduniverse_env.py:136-155) can be
-// tabulated once per level: for every (cell, action) the landing cell plus the goal / lava
-// flags of the landing cell (which give reward and done, :155,163-174).  gu_pack_tables builds
-// the tables on the device with the same transition() code the layout-agnostic kernels use;
-// the rollout kernels copy each env's table into shared memory once per launch and then pay
-// one conflict-free shared load per env step.
+// tabulated once per level.  gu_pack_tables builds the tables on the device with the same
+// transition() code the layout-agnostic kernels use; the rollout kernels stage each env's table in
+// shared memory once per launch and then pay one conflict-free shared load per env step.
 //
 // Formats
-//   NT8  (per-env levels, X*Y <= 64):  one 32-bit word per cell, byte a = landing cell of
-//        action a in bits 0-5, goal flag bit 6, lava flag bit 7 (goal cleared when lava is set:
-//        lava wins, griduniverse_env.py:86-90).  WORD-MAJOR uint32[cells][N].
 //   INFO8 (per-env levels, X*Y <= 256, X <= 127): one byte per cell, bits 0-3 = action a moves the
 //        agent (not a grid edge, not a wall, cell not terminal), bit 6 goal, bit 7 lava of the cell
-//        itself; four cells per 32-bit word, WORD-MAJOR uint32[ceil(cells/4)][N].  A quarter of
-//        NT8's footprint, so four times as many envs stay resident per SM.
+//        itself (goal cleared when lava is set: lava wins, griduniverse_env.py:86-90); four cells per
+//        32-bit word, WORD-MAJOR uint32[ceil(cells/4)][N].  64 bytes per 8x8 env, so a dozen warps of
+//        envs stay resident per SM.  (A next-state table -- landing cell per (cell, action), 256 B per
+//        8x8 env -- needs fewer instructions per step but leaves one warp per scheduler; it measured
+//        6.5 ms against 2.8 ms on BASELINE cfg 4, see profiles/r1_history.md.)
 //   NT16 (shared level, X*Y <= 16383): uint16 per (cell, action): landing in bits 0-13, goal
 //        bit 14, lava bit 15.  uint16[cells][4], read by every env of the batch.
 #include <cuda.h>
@@ -25,38 +23,16 @@
 
 namespace gu {
 
-enum TableFormat { kTableNone = 0, kTableNT8 = 1, kTableNT16 = 2, kTableINFO8 = 3 };
+enum TableFormat { kTableNone = 0, kTableNT16 = 2, kTableINFO8 = 3 };
 
 static TableFormat table_format(const gu_levels* lv) {
   const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
-  static const char* force = getenv("GU_TABLE_FORMAT");   // developer switch for A/B timing
-  if (lv->per_env && cells <= 64 && force && force[0] == 'N') return kTableNT8;
   if (lv->per_env && cells <= 256 && lv->X <= 127) return kTableINFO8;
-  if (lv->per_env && cells <= 64) return kTableNT8;
   if (!lv->per_env && cells <= 16383) return kTableNT16;
   return kTableNone;
 }
 
 // ---- table construction -------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-pack_nt8_kernel(LevelsView lv, uint32_t* __restrict__ tables) {
-  const int64_t env = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (env >= lv.N) return;
-  const int cells = lv.X * lv.Y;
-  for (int s = 0; s < cells; ++s) {
-    uint32_t word = 0;
-#pragma unroll
-    for (int a = 0; a < 4; ++a) {
-      int n, r;
-      bool term;
-      transition(lv, env, s, a, true, n, r, term);
-      const uint32_t f = r == kRewardLava ? 0x80u : (r == kRewardGoal ? 0x40u : 0u);
-      word |= (static_cast<uint32_t>(n) | f) << (8 * a);
-    }
-    tables[static_cast<int64_t>(s) * lv.N + env] = word;
-  }
-}
-
 __global__ void __launch_bounds__(128)
 pack_info8_kernel(LevelsView lv, uint32_t* __restrict__ tables) {
   const int64_t env = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -96,264 +72,7 @@ pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
   tables[i] = static_cast<uint16_t>(static_cast<uint32_t>(n) | f);
 }
 
-// ---- rollout over NT8 tables --------------------------------------------------------------
-// EPT consecutive envs per thread (EPT = 4: actions / outputs move as int4 / uchar4 requests).
-// Shared-memory layout: word of (cell s, env slot k of thread tid) at s*EPB + k*THREADS + tid,
-// EPB = THREADS*EPT, so every shared load of a warp hits 32 different banks.
-// Only a thread's own slots are ever read by it: no barrier is needed after staging.
-constexpr int kNt8Threads = 128;
-constexpr int kNt8Unroll = 8;    // action rows kept in flight per thread (software prefetch)
-
-template <int EPT> struct ActVec;
-template <> struct ActVec<4> { using type = int4; };
-template <> struct ActVec<1> { using type = int; };
-
-__device__ __forceinline__ void unpack_act(const int4& v, int (&a)[4]) { a[0] = v.x; a[1] = v.y; a[2] = v.z; a[3] = v.w; }
-__device__ __forceinline__ void unpack_act(const int& v, int (&a)[1]) { a[0] = v; }
-
-template <int EPT, bool TRAJ>
-__global__ void __launch_bounds__(kNt8Threads)
-rollout_nt8_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restrict__ tables,
-                   const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
-                   int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
-                   const int32_t* __restrict__ start, const int32_t* __restrict__ start_choice,
-                   int32_t* __restrict__ env_return, int32_t* __restrict__ env_done, int64_t* stats,
-                   uint32_t flags) {
-  extern __shared__ uint32_t tab[];
-  using AV = typename ActVec<EPT>::type;
-  constexpr int EPB = kNt8Threads * EPT;
-  const int tid = threadIdx.x;
-  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kNt8Threads + tid) * EPT;
-  const bool live = env0 < N;                 // N % EPT == 0 is guaranteed by the launcher
-  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
-  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
-  long long rsum = 0, dcnt = 0;
-
-  if (live) {
-    // stage this thread's tables: coalesced 16-byte loads of EPT consecutive envs per cell
-    for (int s = 0; s < cells; ++s) {
-      int wv[EPT];
-      unpack_act(*reinterpret_cast<const AV*>(tables + static_cast<int64_t>(s) * N + env0), wv);
-#pragma unroll
-      for (int k = 0; k < EPT; ++k) tab[s * EPB + k * kNt8Threads + tid] = static_cast<uint32_t>(wv[k]);
-    }
-    int p[EPT], st[EPT];
-    unpack_act(*reinterpret_cast<const AV*>(pos + env0), p);
-    unpack_act(*reinterpret_cast<const AV*>(start + env0), st);
-    uint32_t word[EPT], fsum[EPT], fsq[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-      word[k] = tab[p[k] * EPB + k * kNt8Threads + tid];
-      fsum[k] = 0;
-      fsq[k] = 0;
-    }
-    const int32_t* ap = actions + env0;
-    AV abuf[kNt8Unroll];
-#pragma unroll
-    for (int u = 0; u < kNt8Unroll; ++u)
-      if (u < T) abuf[u] = *reinterpret_cast<const AV*>(ap + static_cast<int64_t>(u) * N);
-    for (int64_t t0 = 0; t0 < T; t0 += kNt8Unroll) {
-      AV acur[kNt8Unroll];
-#pragma unroll
-      for (int u = 0; u < kNt8Unroll; ++u) acur[u] = abuf[u];
-      // next batch of action rows goes in flight before this batch is consumed
-#pragma unroll
-      for (int u = 0; u < kNt8Unroll; ++u)
-        if (t0 + kNt8Unroll + u < T)
-          abuf[u] = *reinterpret_cast<const AV*>(ap + (t0 + kNt8Unroll + u) * N);
-#pragma unroll
-      for (int u = 0; u < kNt8Unroll; ++u) {
-        const int64_t t = t0 + u;
-        if (t < T) {
-          int a[EPT];
-          unpack_act(acur[u], a);
-          int ob[EPT], rw[EPT];
-          uint32_t dn[EPT];
-          int sc[EPT];
-          if (start_choice != nullptr) unpack_act(*reinterpret_cast<const AV*>(start_choice + t * N + env0), sc);
-#pragma unroll
-          for (int k = 0; k < EPT; ++k) {
-            // byte (a & 3) of the cell's word: the funnel shift takes its amount modulo 32
-            const uint32_t v = __funnelshift_r(word[k], 0u, static_cast<uint32_t>(a[k]) << 3);
-            const uint32_t f = v & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
-            int n = static_cast<int>(v & 0x3fu);
-            if (TRAJ) {
-              ob[k] = n;
-              rw[k] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
-              dn[k] = f ? 1u : 0u;
-            }
-            fsum[k] += f;                               // 64*goals + 128*lavas
-            fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-            if (auto_reset && f) n = start_choice != nullptr ? sc[k] : st[k];
-            p[k] = n;
-            word[k] = tab[n * EPB + k * kNt8Threads + tid];
-          }
-          if (TRAJ) {
-            const int64_t o = t * N + env0;
-            if (EPT == 4) {
-              if (obs) *reinterpret_cast<int4*>(obs + o) = make_int4(ob[0], ob[1 % EPT], ob[2 % EPT], ob[3 % EPT]);
-              if (reward) *reinterpret_cast<int4*>(reward + o) = make_int4(rw[0], rw[1 % EPT], rw[2 % EPT], rw[3 % EPT]);
-              if (done) *reinterpret_cast<uchar4*>(done + o) = make_uchar4(dn[0], dn[1 % EPT], dn[2 % EPT], dn[3 % EPT]);
-            } else {
-              if (obs) obs[o] = ob[0];
-              if (reward) reward[o] = rw[0];
-              if (done) done[o] = static_cast<uint8_t>(dn[0]);
-            }
-          }
-        }
-      }
-    }
-    int er[EPT], ed[EPT];
-#pragma unroll
-    for (int k = 0; k < EPT; ++k) {
-      const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
-      const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
-      const long long dones = static_cast<long long>(goals) + lavas;
-      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
-      rsum += ret;
-      dcnt += dones;
-      er[k] = static_cast<int>(ret);
-      ed[k] = static_cast<int>(dones);
-    }
-    if (EPT == 4) {
-      *reinterpret_cast<int4*>(pos + env0) = make_int4(p[0], p[1 % EPT], p[2 % EPT], p[3 % EPT]);
-      if (env_return) {
-        int4* q = reinterpret_cast<int4*>(env_return + env0);
-        int4 old = accumulate ? *q : make_int4(0, 0, 0, 0);
-        *q = make_int4(old.x + er[0], old.y + er[1 % EPT], old.z + er[2 % EPT], old.w + er[3 % EPT]);
-      }
-      if (env_done) {
-        int4* q = reinterpret_cast<int4*>(env_done + env0);
-        int4 old = accumulate ? *q : make_int4(0, 0, 0, 0);
-        *q = make_int4(old.x + ed[0], old.y + ed[1 % EPT], old.z + ed[2 % EPT], old.w + ed[3 % EPT]);
-      }
-    } else {
-      pos[env0] = p[0];
-      if (env_return) env_return[env0] = er[0] + (accumulate ? env_return[env0] : 0);
-      if (env_done) env_done[env0] = ed[0] + (accumulate ? env_done[env0] : 0);
-    }
-  }
-  publish_stats(rsum, dcnt, stats);
-}
-
-// ---- rollout over NT8 tables, TMA bulk-copy staged (the fast path) ----------------------------
-// One warp owns 128 consecutive envs; lane l steps envs l, l+32, l+64, l+96 of the warp's range, so a
-// warp's words of one table row / one action row are 512 contiguous bytes in HBM and, copied
-// verbatim into shared memory, are read back conflict-free (bank = lane).  All HBM traffic is
-// issued by one elected lane as cp.async.bulk (TMA, SASS UBLKCP) copies that complete on
-// per-warp mbarriers: the 32 KB transition table once, then the action stream in batches of
-// kBulkRows time steps through a kBulkStages-deep ring, so kBulkStages*8 KB per warp are in
-// flight while the other lanes step.  No block-level barrier: warps are independent.
-constexpr int kBulkWarps = 4;
-constexpr int kBulkRows = 16;      // action rows (time steps) per batch
-constexpr int kBulkStages = 2;
-constexpr int kBulkEnvsPerWarp = 128;
-
-template <bool TRAJ>
-__global__ void __launch_bounds__(kBulkWarps * 32)
-rollout_nt8_bulk_kernel(int64_t N, int64_t T, int cells, const uint32_t* __restrict__ tables,
-                        const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
-                        int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
-                        const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
-                        int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  constexpr int EPW = kBulkEnvsPerWarp, ROWB = EPW * 4;              // 512 bytes per row per warp
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const size_t per_warp = static_cast<size_t>(cells) * ROWB + kBulkStages * kBulkRows * ROWB;
-  uint8_t* wbase = smem_raw + warp * per_warp;
-  uint32_t* tab = reinterpret_cast<uint32_t*>(wbase);                                   // [cells][128]
-  uint32_t* act = reinterpret_cast<uint32_t*>(wbase + static_cast<size_t>(cells) * ROWB);  // [stages][rows][128]
-  __shared__ __align__(8) uint64_t bars[kBulkWarps][kBulkStages + 1];
-  const uint32_t bar_tab = smem_u32(&bars[warp][kBulkStages]);
-  const int64_t env0 = (static_cast<int64_t>(blockIdx.x) * kBulkWarps + warp) * EPW;   // N % 128 == 0
-  const bool live = env0 < N;
-  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
-  const bool accumulate = flags & GU_FLAG_ACCUMULATE;
-  const int64_t nbatch = (T + kBulkRows - 1) / kBulkRows;
-  long long rsum = 0, dcnt = 0;
-
-  if (live) {
-    if (lane == 0) {
-      for (int i = 0; i <= kBulkStages; ++i) mbar_init(smem_u32(&bars[warp][i]), 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    }
-    __syncwarp();
-    auto issue_batch = [&](int64_t b) {          // lane 0 only
-      const int stage = static_cast<int>(b % kBulkStages);
-      const int64_t t0 = b * kBulkRows;
-      const int rows = static_cast<int>(T - t0 < kBulkRows ? T - t0 : kBulkRows);
-      const uint32_t bar = smem_u32(&bars[warp][stage]);
-      mbar_expect_tx(bar, static_cast<uint32_t>(rows) * ROWB);
-      for (int r = 0; r < rows; ++r)
-        bulk_g2s(smem_u32(act + (stage * kBulkRows + r) * EPW), actions + (t0 + r) * N + env0, ROWB, bar);
-    };
-    if (lane == 0) {
-      mbar_expect_tx(bar_tab, static_cast<uint32_t>(cells) * ROWB);
-      for (int s = 0; s < cells; ++s)
-        bulk_g2s(smem_u32(tab + s * EPW), tables + static_cast<int64_t>(s) * N + env0, ROWB, bar_tab);
-      for (int64_t b = 0; b < kBulkStages && b < nbatch; ++b) issue_batch(b);
-    }
-    int p[4], st[4];
-    uint32_t word[4], fsum[4], fsq[4];
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      p[k] = pos[env0 + k * 32 + lane];
-      st[k] = start[env0 + k * 32 + lane];
-      fsum[k] = 0;
-      fsq[k] = 0;
-    }
-    mbar_wait(bar_tab, 0);
-#pragma unroll
-    for (int k = 0; k < 4; ++k) word[k] = tab[p[k] * EPW + k * 32 + lane];
-
-    for (int64_t b = 0; b < nbatch; ++b) {
-      const int stage = static_cast<int>(b % kBulkStages);
-      const int64_t t0 = b * kBulkRows;
-      const int rows = static_cast<int>(T - t0 < kBulkRows ? T - t0 : kBulkRows);
-      mbar_wait(smem_u32(&bars[warp][stage]), static_cast<uint32_t>((b / kBulkStages) & 1));
-      const uint32_t* arow = act + stage * kBulkRows * EPW + lane;
-#pragma unroll 4
-      for (int r = 0; r < rows; ++r) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const uint32_t a = arow[r * EPW + k * 32];
-          // byte (a & 3) of the cell's word: the funnel shift takes its amount modulo 32
-          const uint32_t v = __funnelshift_r(word[k], 0u, a << 3);
-          const uint32_t f = v & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
-          int n = static_cast<int>(v & 0x3fu);
-          if (TRAJ) {
-            const int64_t o = (t0 + r) * N + env0 + k * 32 + lane;
-            if (obs) obs[o] = n;
-            if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
-            if (done) done[o] = f ? 1 : 0;
-          }
-          fsum[k] += f;                               // 64*goals + 128*lavas
-          fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-          if (auto_reset && f) n = st[k];
-          p[k] = n;
-          word[k] = tab[n * EPW + k * 32 + lane];
-        }
-      }
-      __syncwarp();                                   // every lane is done with this stage
-      if (lane == 0 && b + kBulkStages < nbatch) issue_batch(b + kBulkStages);
-    }
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const uint32_t lavas = (fsq[k] - 64u * fsum[k]) >> 13;
-      const uint32_t goals = (fsum[k] - 128u * lavas) >> 6;
-      const long long dones = static_cast<long long>(goals) + lavas;
-      const long long ret = -(T - dones) + 10ll * goals - 10ll * lavas;
-      rsum += ret;
-      dcnt += dones;
-      const int64_t e = env0 + k * 32 + lane;
-      pos[e] = p[k];
-      if (env_return) env_return[e] = static_cast<int>(ret) + (accumulate ? env_return[e] : 0);
-      if (env_done) env_done[e] = static_cast<int>(dones) + (accumulate ? env_done[e] : 0);
-    }
-  }
-  publish_stats(rsum, dcnt, stats);
-}
+constexpr int kBulkWarps = 4;    // warps per block of the TMA rollout kernel (each warp is independent)
 
 // ---- rollout over INFO8 tables, TMA-tiled staging ---------------------------------------------------
 // A warp owns 32*EPT consecutive envs and lane l steps envs l, l+32, ...  All HBM traffic is 2-D
@@ -652,52 +371,6 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
 #undef GU_INFO8
 #undef GU_INFO8_ARGS
   }
-  if (fmt == kTableNT8 && n % kBulkEnvsPerWarp == 0 && start_choice == nullptr && al16(actions) && al16(tables)) {
-    const size_t smem = static_cast<size_t>(kBulkWarps) *
-                        (static_cast<size_t>(cells) * 512 + kBulkStages * kBulkRows * 512);
-    const unsigned blocks = static_cast<unsigned>((n / kBulkEnvsPerWarp + kBulkWarps - 1) / kBulkWarps);
-    if (traj) {
-      cudaError_t e = cudaFuncSetAttribute(rollout_nt8_bulk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-      if (e != cudaSuccess) return static_cast<int>(e);
-      rollout_nt8_bulk_kernel<true><<<blocks, kBulkWarps * 32, smem, st>>>(
-          n, T, cells, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
-    } else {
-      cudaError_t e = cudaFuncSetAttribute(rollout_nt8_bulk_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           static_cast<int>(smem));
-      if (e != cudaSuccess) return static_cast<int>(e);
-      rollout_nt8_bulk_kernel<false><<<blocks, kBulkWarps * 32, smem, st>>>(
-          n, T, cells, tables, actions, pos, obs, reward, done, lv->start, env_return, env_done, stats, flags);
-    }
-    GU_CHECK_LAUNCH();
-    return GU_OK;
-  }
-  if (fmt == kTableNT8) {
-    const bool vec = (n % 4 == 0) && al16(actions) && al16(pos) && al16(tables) && al16(lv->start) &&
-                     (!obs || al16(obs)) && (!reward || al16(reward)) && (!done || al4(done)) &&
-                     (!start_choice || al16(start_choice)) && (!env_return || al16(env_return)) &&
-                     (!env_done || al16(env_done));
-    const int ept = vec ? 4 : 1;
-    const size_t smem = static_cast<size_t>(cells) * 4 * kNt8Threads * ept;
-    const int64_t threads = n / ept;
-    const unsigned blocks = static_cast<unsigned>((threads + kNt8Threads - 1) / kNt8Threads);
-#define GU_NT8(EPT, TRAJ)                                                                                     \
-  do {                                                                                                        \
-    cudaError_t e = cudaFuncSetAttribute(rollout_nt8_kernel<EPT, TRAJ>,                                       \
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)); \
-    if (e != cudaSuccess) return static_cast<int>(e);                                                         \
-    rollout_nt8_kernel<EPT, TRAJ><<<blocks, kNt8Threads, smem, st>>>(n, T, cells, tables, actions, pos, obs,  \
-                                                                     reward, done, lv->start, start_choice,   \
-                                                                     env_return, env_done, stats, flags);     \
-  } while (0)
-    if (vec && traj) GU_NT8(4, true);
-    else if (vec) GU_NT8(4, false);
-    else if (traj) GU_NT8(1, true);
-    else GU_NT8(1, false);
-#undef GU_NT8
-    GU_CHECK_LAUNCH();
-    return GU_OK;
-  }
   if (fmt == kTableNT16) {
     const size_t smem = static_cast<size_t>(cells) * 8;
     const unsigned blocks = static_cast<unsigned>((n + kNt16Threads - 1) / kNt16Threads);
@@ -731,7 +404,6 @@ extern "C" __attribute__((visibility("default"))) int64_t gu_tables_bytes(const 
   if (!lv || n < 0) return 0;
   const int64_t cells = static_cast<int64_t>(lv->X) * lv->Y;
   switch (table_format(lv)) {
-    case kTableNT8: return cells * 4 * n;
     case kTableINFO8: return ((cells + 3) / 4) * 4 * n;
     case kTableNT16: return cells * 8;
     default: return 0;
@@ -746,10 +418,7 @@ extern "C" __attribute__((visibility("default"))) int gu_pack_tables(const gu_le
   (void)flags;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const TableFormat fmt = table_format(lv);
-  if (fmt == kTableNT8) {
-    if (n == 0) return GU_OK;
-    pack_nt8_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(view_of(lv, n), tables);
-  } else if (fmt == kTableINFO8) {
+  if (fmt == kTableINFO8) {
     if (n == 0) return GU_OK;
     pack_info8_kernel<<<static_cast<unsigned>((n + 127) / 128), 128, 0, st>>>(view_of(lv, n), tables);
   } else if (fmt == kTableNT16) {

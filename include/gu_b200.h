@@ -124,8 +124,10 @@ int gu_mc_finalize_f64(int32_t cells, const double* total_visits, const double* 
 
 /* Size in bytes of the transition tables for (lv, n_envs), 0 if the shape has no table format. */
 int64_t gu_tables_bytes(const gu_levels* lv, int64_t n_envs);
-/* Build transition tables (device) from the bit planes: next state per (cell, action)
- * with the landing cell's goal/lava flags, word-major like the planes. */
+/* Build transition tables (device) from the bit planes.  Per-env levels (X*Y <= 256, X <= 127):
+ * one info byte per cell ("action a moves" bits + goal / lava), four cells per word, word-major
+ * like the planes.  Shared level (X*Y <= 16383): landing cell + goal / lava flags per
+ * (cell, action) as uint16. */
 int gu_pack_tables(const gu_levels* lv, int64_t n_envs, uint32_t* tables, uint32_t flags, void* stream);
 
 /* look_step_ahead for M arbitrary (state, action) pairs (griduniverse_env.py:136-155).
