@@ -72,7 +72,10 @@ pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
   tables[i] = static_cast<uint16_t>(static_cast<uint32_t>(n) | f);
 }
 
-constexpr int kBulkWarps = 4;    // warps per block of the TMA rollout kernel (each warp is independent)
+#ifndef GU_ROLLOUT_WARPS
+#define GU_ROLLOUT_WARPS 4
+#endif
+constexpr int kBulkWarps = GU_ROLLOUT_WARPS;    // warps per block of the TMA rollout kernel (each warp is independent)
 
 // ---- rollout over INFO8 tables, TMA-tiled staging ---------------------------------------------------
 // A warp owns 32*EPT consecutive envs and lane l steps envs l, l+32, ...  All HBM traffic is 2-D
