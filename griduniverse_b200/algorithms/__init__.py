@@ -1,1 +1,1 @@
-from . import utils, dynamic_programming, monte_carlo  # noqa: F401
+from . import utils, dynamic_programming, monte_carlo, maze_solving  # noqa: F401

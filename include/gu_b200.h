@@ -229,6 +229,34 @@ int gu_peer_wait(const gu_peer_links* peer, int is_f64, void* stream);
 int gu_greedy_f64(const gu_grid* g, const double* v, uint8_t* tie_mask, double gamma, void* stream);
 int gu_greedy_f32(const gu_grid* g, const float* v, uint8_t* tie_mask, float gamma, void* stream);
 
+/* ---- shortest paths (cross-check of greedy policies) --------------------- */
+
+/* Breadth-first distances over the graph the reference builds with
+ * look_step_ahead(s, a, care_about_terminal=False) on the non-wall cells
+ * (core/algorithms/maze_solving.py:43-50) -- searched there by a FIFO queue from one state to the
+ * first terminal it reaches (:123-168).  Here: a multi-source wavefront, one level per kernel
+ * launch, 32 cells per word.  Whole grids only (row_begin == 0, row_end == Y), pitch ==
+ * 32*pitch_words.  `visited_a` / `visited_b`: uint32[(Y+2)*pitch_words] ping-pong planes;
+ * `dist`: int32[(Y+2)*pitch], 16-byte aligned, -1 = not reached; `reached` (uint64, caller zeroes
+ * it) is incremented by the number of cells each level reaches.
+ *   gu_bfs_init    sources (NULL = the goal plane) restricted to enterable cells get distance 0.
+ *   gu_bfs_expand  runs levels level_begin .. level_begin+n_levels-1 (level_begin >= 1, continuing
+ *                  from the previous call); extra levels after the wavefront died are no-ops, so
+ *                  the caller polls `reached` every chunk of levels instead of every level.
+ *   gu_bfs_walk    the action list of a shortest path from start_state to the nearest source
+ *                  (replaces construct_path, maze_solving.py:170-193): at every step the
+ *                  lowest-numbered action that lands one level closer.  *length = number of
+ *                  actions, -1 if start_state was not reached, -3 if max_len is too small.
+ * GU_BFS_LAVA_BLOCKS: lava cells are not entered (distance to the goal along cells an optimal
+ * policy may use); default: only walls block, as in the reference graph. */
+#define GU_BFS_LAVA_BLOCKS 1u
+int gu_bfs_init(const gu_grid* g, const uint32_t* sources, uint32_t* visited_a, uint32_t* visited_b,
+                int32_t* dist, uint64_t* reached, uint32_t flags, void* stream);
+int gu_bfs_expand(const gu_grid* g, uint32_t* visited_a, uint32_t* visited_b, int32_t* dist,
+                  int32_t level_begin, int32_t n_levels, uint64_t* reached, uint32_t flags, void* stream);
+int gu_bfs_walk(const gu_grid* g, const int32_t* dist, int64_t start_state, int8_t* actions,
+                int32_t max_len, int32_t* length, void* stream);
+
 /* Whole value_iteration loop (dynamic_programming.py:8-28) for a grid small enough to
  * live in one thread block's shared memory (see gu_vi_small_max_cells): sweeps until
  * max(V - V') < threshold or max_steps, then writes V, the tie masks of the final V,

@@ -399,6 +399,121 @@ def monte_carlo_evaluation(policy, level, starts_stream, every_visit=False, incr
 
 
 # --------------------------------------------------------------------------
+# Shortest paths (core/algorithms/maze_solving.py)
+# --------------------------------------------------------------------------
+def bfs_graph(level):
+    """create_graph, maze_solving.py:43-50: for every non-wall state the list of states reached
+    by the four actions with care_about_terminal=False, in action order, self-loops dropped."""
+    nxt = next_table(level, care_about_terminal=False)
+    graph = {}
+    for s in range(level.N):
+        if not level.wall[s]:
+            graph[s] = [int(n) for n in nxt[s] if n != s]
+    return graph
+
+
+def bfs_reference_path(level, start):
+    """breadth_first_search + construct_path + calculate_action, maze_solving.py:110-193: FIFO
+    search from ``start``, stops at the first terminal dequeued, returns the action list (None if
+    no terminal is reachable -- the script then has nothing to return either)."""
+    graph = bfs_graph(level)
+    open_set, closed_set, meta = [start], set(), {start: (None, None)}
+    while open_set:
+        parent = open_set.pop(0)
+        if level.term[parent]:
+            actions = []
+            state = parent
+            while meta[state][0] is not None:
+                state, a = meta[state]
+                actions.append(a)
+            actions.reverse()
+            return actions
+        for child in graph[parent]:
+            if child in closed_set or child in open_set:
+                continue
+            diff = parent - child        # calculate_action, :110-121
+            a = LEFT if diff == 1 else RIGHT if diff == -1 else DOWN if diff < -1 else UP
+            meta[child] = (parent, a)
+            open_set.append(child)
+        closed_set.add(parent)
+    return None
+
+
+def bfs_distances(level, sources, lava_blocks=False):
+    """Distance (number of actions) from every state to the nearest of ``sources`` over the
+    graph of bfs_graph; -1 where no source is reachable and on walls.  ``lava_blocks`` also
+    removes the lava cells from the graph.  Queue version (small levels)."""
+    from collections import deque
+    graph = bfs_graph(level)
+    blocked = level.wall | level.lava if lava_blocks else level.wall
+    dist = np.full(level.N, -1, dtype=np.int32)
+    queue = deque()
+    for s in sources:
+        if not blocked[s] and dist[s] < 0:
+            dist[s] = 0
+            queue.append(int(s))
+    while queue:
+        s = queue.popleft()
+        for n in graph[s]:
+            if dist[n] < 0 and not blocked[n]:
+                dist[n] = dist[s] + 1
+                queue.append(n)
+    return dist
+
+
+def bfs_distances_dense(level, sources, lava_blocks=False):
+    """Same result as bfs_distances by whole-grid wavefront expansion (bigger levels)."""
+    X, Y = level.X, level.Y
+    blocked = (level.wall | level.lava if lava_blocks else level.wall).reshape(Y, X)
+    seen = np.zeros((Y, X), dtype=bool)
+    seen.reshape(-1)[np.asarray(list(sources), dtype=np.int64)] = True
+    seen &= ~blocked
+    dist = np.where(seen, 0, -1).astype(np.int32)
+    d = 0
+    while True:
+        d += 1
+        grow = np.zeros_like(seen)
+        grow[1:] |= seen[:-1]
+        grow[:-1] |= seen[1:]
+        grow[:, 1:] |= seen[:, :-1]
+        grow[:, :-1] |= seen[:, 1:]
+        new = grow & ~seen & ~blocked
+        if not new.any():
+            return dist.reshape(-1)
+        dist[new] = d
+        seen |= new
+
+
+def bfs_descent_path(level, dist, start):
+    """Shortest path from ``start`` down a distance field: lowest-numbered action that lands one
+    level closer (the np.argmax order, examples/griduniverse_alg_examples.py:76)."""
+    if dist[start] < 0:
+        return None
+    s, actions = int(start), []
+    while dist[s] > 0:
+        for a in range(4):
+            n = clamp_move(level, s, a)
+            if n != s and dist[n] == dist[s] - 1:
+                actions.append(a)
+                s = n
+                break
+        else:
+            raise ValueError("not a distance field of this level")
+    return actions
+
+
+def value_from_goal_distance(d, gamma=0.9):
+    """Fixed point of value_iteration (dynamic_programming.py:8-28) in closed form for a state
+    ``d`` actions from the nearest goal along non-lava cells: d step rewards of -1 discounted by
+    gamma (utils.py:23 pays the reward of the CURRENT state), then the goal's own value 10 (its
+    greedy row is all zero, utils.py:69-71).  A state that cannot reach a goal pays -1 forever."""
+    d = np.asarray(d, dtype=np.float64)
+    reach = d >= 0
+    gd = np.power(gamma, np.where(reach, d, 0.0))
+    return np.where(reach, -(1.0 - gd) / (1.0 - gamma) + gd * REWARD_GOAL, REWARD_STEP / (1.0 - gamma))
+
+
+# --------------------------------------------------------------------------
 # ASCII render (griduniverse_env.py:202-221) -- host glue, kept for the unit-test goldens
 # --------------------------------------------------------------------------
 def render_ansi(level, current_state):

@@ -80,3 +80,82 @@ def test_greedy_rollout_return_matches_value_function():
     stuck = np.flatnonzero(~done)
     if stuck.size:
         assert np.all(np.abs(V[starts[stuck]] + 10.0) < 1e-5)
+
+
+@pytest.mark.parametrize("shape,n,T", [((16, 16), 65536, 1024), ((8, 8), 16777216, 64)])
+def test_full_size_env_batches(shape, n, T):
+    """BASELINE cfg 3 (full size) and cfg 4 (all 16.7 M envs, shorter horizon): the batch counters agree
+    with the per-env summaries, and a 1,024-env subset replayed through the oracle matches exactly."""
+    from oracle import gu_oracle as orc
+    from griduniverse_b200.envs import GridUniverseVecEnv
+    X, Y = shape
+    levels = synth.env_levels_device(X, Y, n, seed=0)
+    env = GridUniverseVecEnv(n, levels=levels, auto_reset=True)
+    assert env.levels.tables is not None
+    env.reset()
+    gen = torch.Generator(device="cuda").manual_seed(1)
+    actions = torch.randint(0, 4, (T, n), dtype=torch.int32, device="cuda", generator=gen)
+    out = env.rollout(actions, per_env=True)
+    assert int(out["stats"][0]) == int(out["env_return"].sum(dtype=torch.int64))
+    assert int(out["stats"][1]) == int(out["env_done"].sum(dtype=torch.int64))
+    assert int(out["env_done"].max()) <= T and int(out["env_return"].max()) <= 10 * T
+    # every env is where a legal walk can be: never on a wall cell
+    pos = out["pos"].long()
+    wall_word = levels.wall.view(levels.words, n)[pos >> 5, torch.arange(n, device="cuda")]
+    assert not bool(((wall_word >> (pos & 31)) & 1).any())
+    idx = np.arange(1024) * (n // 1024) + 7
+    sub_actions = actions[:, torch.from_numpy(idx).cuda()].cpu().numpy()
+    olevels, starts = [], []
+    for i in idx:
+        w, g, l, s = synth.env_levels_numpy(X, Y, 1, first_env=int(i), seed=0)
+        olevels.append(orc.Level.from_masks(X, Y, w[0], g[0], l[0], [int(s[0])]))
+        starts.append(int(s[0]))
+    _, er, ed, ep = orc.rollout(olevels, np.array(starts), sub_actions, auto_reset=True)
+    assert np.array_equal(out["pos"].cpu().numpy()[idx], ep)
+    assert np.array_equal(out["env_return"].cpu().numpy()[idx], er.sum(axis=0))
+    assert np.array_equal(out["env_done"].cpu().numpy()[idx], ed.sum(axis=0))
+
+
+def test_full_size_values_match_breadth_first_distances():
+    """Second, independent oracle at 16384 x 16384: the fixed point of value
+    iteration is a closed form of the breadth-first distance d to the goal along non-lava cells,
+    V = -(1 - g^d)/(1 - g) + 10 g^d, and -1/(1 - g) where no goal is reachable.  After k sweeps
+    the iterate is within 30 g^k of it (k = 130: 3.4e-5), plus fp32 rounding."""
+    from griduniverse_b200.paths import ShortestPaths
+    size, gamma, theta = 16384, 0.9, 1e-6
+    grid = synth.maze_plan_grid(size, size, seed=0, dtype=np.float32)
+    pl = Planner(None, np.float32, "cuda", grid=grid)
+    v, tie, sweeps, _ = pl.value_iteration("uniform", None, theta, 1000, gamma)
+    sp = ShortestPaths(grid, chunk=512)
+    dist = sp.solve(None, lava_blocks=True)
+    assert sp.reached > 0.3 * size * size and sp.levels > size // 2     # the maze percolates
+    d = dist.to(torch.float64)
+    gd = torch.pow(torch.tensor(gamma, dtype=torch.float64, device="cuda"), d.clamp(min=0))
+    closed = torch.where(d >= 0, -(1.0 - gd) / (1.0 - gamma) + 10.0 * gd, torch.full_like(d, -1.0 / (1.0 - gamma)))
+    info = grid.info.view(grid.rows + 2, grid.pitch)
+    check = torch.zeros_like(info, dtype=torch.bool)
+    wall = torch.zeros_like(check)
+    bits = grid.wall.view(grid.rows + 2, grid.pitch_words)
+    for b in range(32):
+        wall[:, b::32] = ((bits >> b) & 1).bool()
+    check[1:-1, :size] = True
+    check &= ~wall & ((info & 24) == 0)
+    assert int(check.sum()) > 0.6 * size * size
+    err = (v.to(torch.float64) - closed).abs()
+    assert err[check].max().item() < 2e-4
+    # the executed greedy action (ctz of the tie mask) lands one level closer to the goal wherever
+    # one level is worth far more than fp32 rounding (2 g^(d-1) > 2e-3 for d < 64)
+    near = check & (dist > 0) & (dist < 64)
+    act = torch.zeros_like(dist)
+    for a in (3, 2, 1, 0):
+        act = torch.where(((tie >> a) & 1).bool(), torch.full_like(act, a), act)
+    nd = torch.full_like(dist, -1)
+    nd[1:-1] = torch.where(act[1:-1] == 0, dist[:-2], torch.where(act[1:-1] == 2, dist[2:], nd[1:-1]))
+    nd[:, :-1] = torch.where(act[:, :-1] == 1, dist[:, 1:], nd[:, :-1])
+    nd[:, 1:] = torch.where(act[:, 1:] == 3, dist[:, :-1], nd[:, 1:])
+    assert torch.all(nd[near] == dist[near] - 1)
+    # a shortest action list from the farthest reached cell really ends on the goal
+    far = int(torch.argmax(dist.view(-1)).item())
+    fy, fx = divmod(far, grid.pitch)
+    path = sp.walk((fy - 1) * size + fx)
+    assert len(path) == sp.levels
