@@ -13,7 +13,10 @@
 namespace gu {
 
 constexpr int kBfsThreads = 128;
-constexpr int kBfsRows = 8;   // rows walked by one thread (register window over up / cur / down words)
+#ifndef GU_BFS_ROWS
+#define GU_BFS_ROWS 4
+#endif
+constexpr int kBfsRows = GU_BFS_ROWS;   // rows walked by one thread (register window over up / cur / down quads)
 
 __device__ __forceinline__ uint32_t column_mask(const GridView& g, int w) {
   const int first = w << 5;
@@ -38,7 +41,11 @@ bfs_init_kernel(GridView g, const uint32_t* __restrict__ sources, uint32_t* __re
   const int ar = blockIdx.y;
   const int rows = g.row_end - g.row_begin;
   uint32_t src = 0;
-  if (w < g.pitch_words) {
+  if (w >= (g.pitch >> 5) && w < g.pitch_words) {   // row padding words: stay zero, no dist storage
+    visited[static_cast<size_t>(ar) * g.pitch_words + w] = 0u;
+    visited_b[static_cast<size_t>(ar) * g.pitch_words + w] = 0u;
+  }
+  if (w < (g.pitch >> 5)) {
     const size_t idx = static_cast<size_t>(ar) * g.pitch_words + w;
     if (ar >= 1 && ar <= rows) src = (sources ? sources[idx] : g.goal[idx]) & open_word(g, idx, w, lava_blocks);
     visited[idx] = src;
@@ -56,45 +63,59 @@ bfs_init_kernel(GridView g, const uint32_t* __restrict__ sources, uint32_t* __re
   if ((threadIdx.x & 31) == 0 && n) atomicAdd(reached, static_cast<unsigned long long>(n));
 }
 
-// one search level: vout = vin | (neighbours(vin) & open); new bits get dist = level
+// one search level: vout = vin | (neighbours(vin) & open); new bits get dist = level.
+// A thread owns a quad of 4 words (128 cells, one 16-byte load) and walks kBfsRows rows with the
+// up / cur / down quads in registers; the words left and right of the quad come from the
+// neighbouring lanes.  Words at and beyond pitch/32 are row padding: open_word() is 0 there.
 __global__ void __launch_bounds__(kBfsThreads)
 bfs_expand_kernel(GridView g, const uint32_t* __restrict__ vin, uint32_t* __restrict__ vout,
                   int32_t* __restrict__ dist, int level, bool lava_blocks,
                   unsigned long long* __restrict__ reached) {
-  const int w = blockIdx.x * kBfsThreads + threadIdx.x;
+  const int q = blockIdx.x * kBfsThreads + threadIdx.x;        // quad column
   const int lane = threadIdx.x & 31;
   const int rows = g.row_end - g.row_begin;
   const int ar0 = 1 + blockIdx.y * kBfsRows;                    // first array row of this thread
   const int ar1 = min(ar0 + kBfsRows, rows + 1);
-  const bool in = w < g.pitch_words;
-  const int pw = g.pitch_words;
-  auto word = [&](int ar, int ww) -> uint32_t {                // ghost rows hold zeros
-    return vin[static_cast<size_t>(ar) * pw + ww];
+  const int pw = g.pitch_words, nq = pw >> 2;
+  const bool in = q < nq;
+  const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
+  auto quad = [&](int ar) -> uint4 {                            // ghost rows hold zeros
+    return reinterpret_cast<const uint4*>(vin + static_cast<size_t>(ar) * pw)[q];
   };
-  uint32_t up = in ? word(ar0 - 1, w) : 0u;
-  uint32_t cur = in ? word(ar0, w) : 0u;
+  uint4 up = in ? quad(ar0 - 1) : zero;
+  uint4 cur = in ? quad(ar0) : zero;
   unsigned fresh = 0;
   for (int ar = ar0; ar < ar1; ++ar) {
-    const uint32_t dn = in ? word(ar + 1, w) : 0u;
-    uint32_t lw = __shfl_up_sync(0xffffffffu, cur, 1);
-    uint32_t rw = __shfl_down_sync(0xffffffffu, cur, 1);
-    if (lane == 0) lw = (in && w > 0) ? word(ar, w - 1) : 0u;
-    if (lane == 31) rw = (w + 1 < pw) ? word(ar, w + 1) : 0u;
+    const uint4 dn = in ? quad(ar + 1) : zero;
+    uint32_t lw = __shfl_up_sync(0xffffffffu, cur.w, 1);
+    uint32_t rw = __shfl_down_sync(0xffffffffu, cur.x, 1);
+    if (lane == 0) lw = (in && q > 0) ? vin[static_cast<size_t>(ar) * pw + 4 * q - 1] : 0u;
+    if (lane == 31) rw = (q + 1 < nq) ? vin[static_cast<size_t>(ar) * pw + 4 * q + 4] : 0u;
     if (in) {
-      const size_t idx = static_cast<size_t>(ar) * pw + w;
-      const uint32_t nb = up | dn | (cur << 1) | (lw >> 31) | (cur >> 1) | (rw << 31);
-      uint32_t nw = 0;
-      if (nb & ~cur) nw = nb & ~cur & open_word(g, idx, w, lava_blocks);
-      vout[idx] = cur | nw;
-      if (nw) {
-        fresh += __popc(nw);
-        int32_t* d = dist + static_cast<size_t>(ar) * g.pitch + (w << 5);
-        do {
-          const int b = __ffs(nw) - 1;
-          nw &= nw - 1;
-          d[b] = level;
-        } while (nw);
+      const size_t idx = static_cast<size_t>(ar) * pw + 4 * q;
+      uint32_t nw[4];
+      nw[0] = (up.x | dn.x | (cur.x << 1) | (lw >> 31) | (cur.x >> 1) | (cur.y << 31)) & ~cur.x;
+      nw[1] = (up.y | dn.y | (cur.y << 1) | (cur.x >> 31) | (cur.y >> 1) | (cur.z << 31)) & ~cur.y;
+      nw[2] = (up.z | dn.z | (cur.z << 1) | (cur.y >> 31) | (cur.z >> 1) | (cur.w << 31)) & ~cur.z;
+      nw[3] = (up.w | dn.w | (cur.w << 1) | (cur.z >> 31) | (cur.w >> 1) | (rw << 31)) & ~cur.w;
+      if (nw[0] | nw[1] | nw[2] | nw[3]) {                      // candidates: now look at the masks
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          if (nw[k]) nw[k] &= open_word(g, idx + k, 4 * q + k, lava_blocks);
+          uint32_t m = nw[k];
+          if (m) {
+            fresh += __popc(m);
+            int32_t* d = dist + static_cast<size_t>(ar) * g.pitch + ((4 * q + k) << 5);
+            do {
+              const int b = __ffs(m) - 1;
+              m &= m - 1;
+              d[b] = level;
+            } while (m);
+          }
+        }
       }
+      reinterpret_cast<uint4*>(vout + static_cast<size_t>(ar) * pw)[q] =
+          make_uint4(cur.x | nw[0], cur.y | nw[1], cur.z | nw[2], cur.w | nw[3]);
     }
     up = cur;
     cur = dn;
@@ -142,7 +163,8 @@ static inline int bfs_args_ok(const gu_grid* g) {
   if (!g || !g->wall || !g->goal || !g->lava) return GU_ERR_NULL;
   if (g->X <= 0 || g->Y <= 0 || g->row_end <= g->row_begin) return GU_ERR_SHAPE;
   if (g->row_begin != 0 || g->row_end != g->Y) return GU_ERR_UNSUPPORTED;     // whole grids only
-  if (g->pitch != g->pitch_words * 32 || g->pitch < g->X) return GU_ERR_ALIGN;
+  if (g->pitch % 32 != 0 || g->pitch > g->pitch_words * 32 || g->pitch < g->X) return GU_ERR_ALIGN;
+  if (g->pitch_words % 4 != 0) return GU_ERR_ALIGN;                            // rows move as 16-byte quads
   if ((g->Y + kBfsRows - 1) / kBfsRows > 65535 || g->Y + 2 > 65535) return GU_ERR_SHAPE;
   return GU_OK;
 }
@@ -175,7 +197,8 @@ extern "C" __attribute__((visibility("default"))) int gu_bfs_expand(
   if (!visited_a || !visited_b || !dist || !reached) return GU_ERR_NULL;
   if (flags & ~static_cast<uint32_t>(GU_BFS_LAVA_BLOCKS)) return GU_ERR_MODE;
   if (level_begin < 1 || n_levels < 0) return GU_ERR_SHAPE;
-  dim3 grid((g->pitch_words + kBfsThreads - 1) / kBfsThreads, (g->Y + kBfsRows - 1) / kBfsRows);
+  if ((reinterpret_cast<uintptr_t>(visited_a) | reinterpret_cast<uintptr_t>(visited_b)) & 15u) return GU_ERR_ALIGN;
+  dim3 grid((g->pitch_words / 4 + kBfsThreads - 1) / kBfsThreads, (g->Y + kBfsRows - 1) / kBfsRows);
   const GridView v = bview(g);
   for (int32_t k = 0; k < n_levels; ++k) {
     const int32_t level = level_begin + k;

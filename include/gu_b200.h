@@ -235,8 +235,8 @@ int gu_greedy_f32(const gu_grid* g, const float* v, uint8_t* tie_mask, float gam
  * look_step_ahead(s, a, care_about_terminal=False) on the non-wall cells
  * (core/algorithms/maze_solving.py:43-50) -- searched there by a FIFO queue from one state to the
  * first terminal it reaches (:123-168).  Here: a multi-source wavefront, one level per kernel
- * launch, 32 cells per word.  Whole grids only (row_begin == 0, row_end == Y), pitch ==
- * 32*pitch_words.  `visited_a` / `visited_b`: uint32[(Y+2)*pitch_words] ping-pong planes;
+ * launch, 32 cells per word.  Whole grids only (row_begin == 0, row_end == Y), pitch % 32 == 0,
+ * pitch <= 32*pitch_words, pitch_words % 4 == 0, planes 16-byte aligned.  `visited_a` / `visited_b`: uint32[(Y+2)*pitch_words] ping-pong planes;
  * `dist`: int32[(Y+2)*pitch], 16-byte aligned, -1 = not reached; `reached` (uint64, caller zeroes
  * it) is incremented by the number of cells each level reaches.
  *   gu_bfs_init    sources (NULL = the goal plane) restricted to enterable cells get distance 0.

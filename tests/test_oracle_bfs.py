@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "golden", "bfs_cases.json")) as f:
     BFS_CASES = json.load(f)["cases"]
 with open(os.path.join(HERE, "golden", "levels.json")) as f:
-    LEVELS = json.load(f)
+    LEVELS = {k: orc.strip_level_lines(v) for k, v in json.load(f).items()}
 
 
 def replay(level, start, actions):
@@ -35,7 +35,7 @@ def test_reference_paths(case):
     assert level.term[replay(level, case["start"], mine)] and level.term[replay(level, case["start"], case["path"])]
 
 
-@pytest.mark.parametrize("name", ["test_env", "maze_11x11", "maze_21x21"])
+@pytest.mark.parametrize("name", ["test_env", "maze_11x11", "maze_21x21", "maze_101x101"])
 def test_value_iteration_fixed_point_is_the_distance_formula(name):
     level = orc.parse_level_text(LEVELS[name])
     V = orc.value_iteration(np.ones((level.N, 4)) / 4, level, threshold=1e-6, discount_factor=0.9)[0]
