@@ -51,7 +51,63 @@ step_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restr
       if (done) done[i0] = d[0];
     }
   }
-  publish_stats(rsum, dcnt, stats);
+  publish_stats_block(rsum, dcnt, stats);
+}
+
+// Per-env levels of at most 64 cells (cfg 4: 8x8): the whole level is WORDS words per plane, so
+// instead of chasing pos -> wall word -> landing cell -> goal / lava word (three dependent
+// loads), a thread fetches every plane word of its four envs up front as independent 16-byte
+// requests and does the step on 64-bit masks in registers.  Same bytes, no dependent chain.
+template <int WORDS>
+__global__ void __launch_bounds__(256)
+step_small_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+                  int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
+                  const int32_t* __restrict__ start_choice, int64_t* stats, uint32_t flags) {
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
+  const bool care = !(flags & GU_FLAG_NO_CARE_TERMINAL);
+  const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
+  long long rsum = 0, dcnt = 0;
+  if (i0 < lv.N) {
+    const int4 av = *reinterpret_cast<const int4*>(actions + i0);
+    const int4 sv = *reinterpret_cast<const int4*>(pos + i0);
+    uint4 pw[WORDS], pg[WORDS], pl[WORDS];
+#pragma unroll
+    for (int k = 0; k < WORDS; ++k) {
+      pw[k] = __ldg(reinterpret_cast<const uint4*>(lv.wall + k * lv.N + i0));
+      pg[k] = __ldg(reinterpret_cast<const uint4*>(lv.goal + k * lv.N + i0));
+      pl[k] = __ldg(reinterpret_cast<const uint4*>(lv.lava + k * lv.N + i0));
+    }
+    const int a[4] = {av.x, av.y, av.z, av.w};
+    const int s[4] = {sv.x, sv.y, sv.z, sv.w};
+    int n[4], r[4], nxt[4];
+    bool d[4];
+    auto lane_of = [](const uint4& v, int e) -> uint32_t { return e == 0 ? v.x : e == 1 ? v.y : e == 2 ? v.z : v.w; };
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      unsigned long long W = lane_of(pw[0], e), G = lane_of(pg[0], e), L = lane_of(pl[0], e);
+      if (WORDS == 2) {
+        W |= static_cast<unsigned long long>(lane_of(pw[1], e)) << 32;
+        G |= static_cast<unsigned long long>(lane_of(pg[1], e)) << 32;
+        L |= static_cast<unsigned long long>(lane_of(pl[1], e)) << 32;
+      }
+      const unsigned long long Tm = G | L;
+      const bool stay = care && ((Tm >> s[e]) & 1ull);
+      const int c = clamp_move(s[e], a[e], lv.X, lv.Y);
+      n[e] = (stay || ((W >> c) & 1ull)) ? s[e] : c;
+      const bool g = (G >> n[e]) & 1ull, l = (L >> n[e]) & 1ull;
+      r[e] = reward_of(g, l);
+      d[e] = g | l;
+      nxt[e] = n[e];
+      if (auto_reset && d[e]) nxt[e] = start_choice ? __ldg(start_choice + i0 + e) : __ldg(lv.start + i0 + e);
+      rsum += r[e];
+      dcnt += d[e] ? 1 : 0;
+    }
+    *reinterpret_cast<int4*>(pos + i0) = make_int4(nxt[0], nxt[1], nxt[2], nxt[3]);
+    if (obs) *reinterpret_cast<int4*>(obs + i0) = make_int4(n[0], n[1], n[2], n[3]);
+    if (reward) *reinterpret_cast<int4*>(reward + i0) = make_int4(r[0], r[1], r[2], r[3]);
+    if (done) *reinterpret_cast<uchar4*>(done + i0) = make_uchar4(d[0], d[1], d[2], d[3]);
+  }
+  publish_stats_block(rsum, dcnt, stats);
 }
 
 // ---- T steps per launch, layout-agnostic version ------------------------------------------
@@ -157,7 +213,15 @@ extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* l
   const LevelsView v = view_of(lv, n);
   const bool vec = (n % 4 == 0) && aligned16(actions) && aligned16(pos) && (!obs || aligned16(obs)) &&
                    (!reward || aligned16(reward)) && (!done || aligned4(done));
-  if (vec) {
+  const bool small = vec && lv->per_env && lv->words <= 2 && aligned16(lv->wall) && aligned16(lv->goal) &&
+                     aligned16(lv->lava);
+  if (small) {
+    const unsigned blocks = static_cast<unsigned>((n / 4 + 255) / 256);
+    if (lv->words == 1)
+      step_small_kernel<1><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
+    else
+      step_small_kernel<2><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
+  } else if (vec) {
     const int64_t threads = n / 4;
     step_kernel<4><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
         v, actions, pos, obs, reward, done, start_choice, stats, flags);

@@ -81,4 +81,33 @@ __device__ __forceinline__ void publish_stats(long long rsum, long long dcnt, in
   }
 }
 
+// Block-wide variant for the one-step kernels: with a single step per launch the counters are
+// the only same-address traffic, and one atomic pair per warp (N/128 pairs) serialises in L2 for
+// longer than the step itself takes.  Every thread of the block must call this.
+__device__ __forceinline__ void publish_stats_block(long long rsum, long long dcnt, int64_t* stats) {
+  if (stats == nullptr) return;
+  __shared__ long long part[2][32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+    dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = (blockDim.x + 31) >> 5;
+  if (lane == 0) { part[0][warp] = rsum; part[1][warp] = dcnt; }
+  __syncthreads();
+  if (warp == 0) {
+    rsum = lane < nwarps ? part[0][lane] : 0;
+    dcnt = lane < nwarps ? part[1][lane] : 0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      rsum += __shfl_xor_sync(0xffffffffu, rsum, o);
+      dcnt += __shfl_xor_sync(0xffffffffu, dcnt, o);
+    }
+    if (lane == 0) {
+      if (rsum != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats), static_cast<unsigned long long>(rsum));
+      if (dcnt != 0) atomicAdd(reinterpret_cast<unsigned long long*>(stats + 1), static_cast<unsigned long long>(dcnt));
+    }
+  }
+}
+
 }  // namespace gu

@@ -1,0 +1,67 @@
+// gu_level_text.cu -- batched level-text packing on the device.
+//
+// The reference turns one text level into python lists with a row-major character scan
+// (core/envs/griduniverse_env.py:253-300): 'o' floor, '#' wall, 'G' goal, 'L' lava, 'x' start,
+// anything else raises; afterwards a level without a start or without a goal raises.  For a batch
+// of same-shaped levels the scan is a ballot: one warp per level, lane l looks at cell 32k + l and
+// the warp votes one word of each bit plane per step.  Output is the word-major per-env layout of
+// gu_levels; the per-level status carries what the reference would have raised.
+#include "gu_common.cuh"
+
+namespace gu {
+
+constexpr int kTextWarps = 4;
+
+__global__ void __launch_bounds__(kTextWarps * 32)
+pack_level_text_kernel(const uint8_t* __restrict__ text, long long n, int cells, int words,
+                       uint32_t* __restrict__ wall, uint32_t* __restrict__ goal, uint32_t* __restrict__ lava,
+                       int32_t* __restrict__ start, int32_t* __restrict__ n_starts, int32_t* __restrict__ status) {
+  const long long lvl = static_cast<long long>(blockIdx.x) * kTextWarps + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (lvl >= n) return;
+  const uint8_t* t = text + lvl * cells;
+  int first_start = -1, starts = 0, goals = 0, first_bad = -1;
+  for (int k = 0; k < words; ++k) {
+    const int c = k * 32 + lane;
+    const int ch = c < cells ? t[c] : 'o';
+    const uint32_t w = __ballot_sync(0xffffffffu, ch == '#');
+    const uint32_t g = __ballot_sync(0xffffffffu, ch == 'G');
+    const uint32_t l = __ballot_sync(0xffffffffu, ch == 'L');
+    const uint32_t x = __ballot_sync(0xffffffffu, ch == 'x');
+    const uint32_t bad = ~(w | g | l | x | __ballot_sync(0xffffffffu, ch == 'o'));
+    if (lane == 0) {
+      wall[static_cast<size_t>(k) * n + lvl] = w;
+      goal[static_cast<size_t>(k) * n + lvl] = g;
+      lava[static_cast<size_t>(k) * n + lvl] = l;
+    }
+    if (x && first_start < 0) first_start = k * 32 + __ffs(x) - 1;
+    starts += __popc(x);
+    goals += __popc(g);
+    if (bad && first_bad < 0) first_bad = k * 32 + __ffs(bad) - 1;
+  }
+  if (lane == 0) {
+    start[lvl] = first_start < 0 ? 0 : first_start;
+    if (n_starts) n_starts[lvl] = starts;
+    // the reference's order: invalid character during the scan, then no start, then no goal
+    status[lvl] = first_bad >= 0 ? first_bad + 1 : (starts == 0 ? GU_TEXT_NO_START : (goals == 0 ? GU_TEXT_NO_GOAL : 0));
+  }
+}
+
+}  // namespace gu
+
+using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_pack_level_text(
+    const uint8_t* text, int64_t n_levels, int32_t X, int32_t Y, uint32_t* wall, uint32_t* goal, uint32_t* lava,
+    int32_t* start, int32_t* n_starts, int32_t* status, void* stream) {
+  if (n_levels == 0) return GU_OK;
+  if (!text || !wall || !goal || !lava || !start || !status) return GU_ERR_NULL;
+  if (X <= 0 || Y <= 0 || n_levels < 0 || static_cast<int64_t>(X) * Y > (1 << 24)) return GU_ERR_SHAPE;
+  const int cells = X * Y, words = (cells + 31) / 32;
+  const long long blocks = (n_levels + kTextWarps - 1) / kTextWarps;
+  if (blocks > 2147483647LL) return GU_ERR_SHAPE;
+  pack_level_text_kernel<<<static_cast<unsigned>(blocks), kTextWarps * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      text, n_levels, cells, words, wall, goal, lava, start, n_starts, status);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

@@ -70,6 +70,54 @@ class EnvLevels(object):
         lava = np.stack([lv.lava for lv in levels])
         return cls.from_masks(X, Y, wall, goal, lava, [lv.starting_states[0] for lv in levels], device)
 
+    @classmethod
+    def from_text(cls, texts, device="cuda"):
+        """Per-env levels from a batch of level texts (each a list of lines or one string), packed
+        on the device by gu_pack_level_text.  Whitespace handling and the rectangle check are host
+        work (griduniverse_env.py:248-249,278-279); the character scan and the start / goal checks
+        run in the kernel and raise the reference's ValueErrors for the first offending level."""
+        dev = _require_cuda(device)
+        batch = []
+        for t in texts:
+            lines = t.splitlines() if isinstance(t, str) else list(t)
+            lines = ["".join(line.split()) for line in lines]
+            lines = [line for line in lines if line]
+            if not lines or any(len(line) != len(lines[0]) for line in lines):
+                raise ValueError("Input text file is not a rectangle")
+            batch.append(lines)
+        X, Y = len(batch[0][0]), len(batch[0])
+        if any(len(b) != Y or len(b[0]) != X for b in batch):
+            raise ValueError("all levels of a batch share one shape")
+        n, cells = len(batch), X * Y
+        words = (cells + 31) // 32
+        raw = "".join("".join(b) for b in batch).encode("latin-1", "replace")
+        text = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(dev)
+        lv = cls.__new__(cls)
+        lv.device, lv.X, lv.Y, lv.cells, lv.words, lv.per_env, lv.n_levels = dev, X, Y, cells, words, True, n
+        lv.wall = torch.empty(words * n, dtype=torch.int32, device=dev)
+        lv.goal = torch.empty(words * n, dtype=torch.int32, device=dev)
+        lv.lava = torch.empty(words * n, dtype=torch.int32, device=dev)
+        lv.start = torch.empty(n, dtype=torch.int32, device=dev)
+        lv.n_starts = torch.empty(n, dtype=torch.int32, device=dev)
+        status = torch.empty(n, dtype=torch.int32, device=dev)
+        rc = _cabi.lib().gu_pack_level_text(_cabi.ptr(text), n, X, Y, _cabi.ptr(lv.wall), _cabi.ptr(lv.goal),
+                                            _cabi.ptr(lv.lava), _cabi.ptr(lv.start), _cabi.ptr(lv.n_starts),
+                                            _cabi.ptr(status), _cabi.stream_ptr())
+        _cabi.check("gu_pack_level_text", rc)
+        bad = torch.nonzero(status)
+        if bad.numel():
+            i = int(bad[0])
+            code = int(status[i])
+            if code > 0:
+                raise ValueError('Invalid Character "{}". Returning'.format("".join(batch[i])[code - 1]))
+            if code == _cabi.GU_TEXT_NO_START:
+                raise ValueError("No starting states set in text file. Place \"x\" within grid. ")
+            raise ValueError("No terminal goal states set in text file. Place \"T\" within grid. ")
+        lv.desc = _cabi.GuLevels(X, Y, 1, words, lv.wall.data_ptr(), lv.goal.data_ptr(), lv.lava.data_ptr(),
+                                 lv.start.data_ptr())
+        lv.tables = None
+        return lv
+
     def ref(self):
         return ctypes.byref(self.desc)
 

@@ -136,6 +136,18 @@ int gu_pack_tables(const gu_levels* lv, int64_t n_envs, uint32_t* tables, uint32
 int gu_look_step_ahead(const gu_levels* lv, int64_t m, const int32_t* states, const int32_t* actions,
                        int32_t* next, int32_t* reward, uint8_t* terminal, uint32_t flags, void* stream);
 
+/* Batched level text -> per-env bit planes (griduniverse_env.py:253-300): `text` holds n_levels
+ * levels of X*Y characters each, whitespace already removed (:248-249), row-major.  Writes the
+ * word-major planes of a per-env `gu_levels` -- uint32[words][n_levels] --, the first start state of
+ * each level (`start`), optionally how many 'x' it has (`n_starts`, may be NULL), and per level
+ * `status`: 0 = ok; k > 0 = character k-1 is not one of "o#GLx" (ValueError, :292-293);
+ * GU_TEXT_NO_START / GU_TEXT_NO_GOAL = the two ValueErrors raised after the scan (:297-300). */
+#define GU_TEXT_NO_START (-1)
+#define GU_TEXT_NO_GOAL (-2)
+int gu_pack_level_text(const uint8_t* text, int64_t n_levels, int32_t X, int32_t Y, uint32_t* wall,
+                       uint32_t* goal, uint32_t* lava, int32_t* start, int32_t* n_starts,
+                       int32_t* status, void* stream);
+
 /* ---- whole-grid planning ------------------------------------------------ */
 
 /* One grid, or one row shard of it, for the sweep / greedy kernels.

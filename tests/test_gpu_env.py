@@ -127,7 +127,7 @@ def test_cfg1_default_env_1000_steps(golden):
 
 
 @pytest.mark.parametrize("shape,n,T", [((8, 8), 1024, 96), ((16, 16), 1024, 128), ((8, 8), 1001, 33),
-                                       ((5, 7), 130, 50)])
+                                       ((5, 7), 130, 50), ((5, 6), 64, 40), ((7, 9), 256, 40)])
 @pytest.mark.parametrize("auto_reset", [True, False])
 def test_per_env_levels_vs_oracle(shape, n, T, auto_reset):
     """cfg 3 / cfg 4 shapes (and ragged sizes): per-env synthetic levels, random actions."""
@@ -228,3 +228,49 @@ def test_maximum_table_shapes():
     out = env.rollout(acts, trajectories=True)
     eo, er, ed, ep = orc.rollout(olv, np.full(512, lvl.starting_states[0]), acts, auto_reset=True)
     assert np.array_equal(out["obs"], eo) and np.array_equal(out["reward"], er) and np.array_equal(out["pos"], ep)
+
+
+def test_batched_level_text_packing(golden_levels):
+    """gu_pack_level_text against the host parser (itself checked against the reference's goldens):
+    same planes, same first start, same ValueErrors in the reference's order."""
+    from griduniverse_b200.level import parse_level_text
+    from griduniverse_b200.synth import random_maze_lines
+    rng = random.Random(5)
+    for (w, h) in ((7, 9), (16, 16), (33, 5)):
+        texts = [random_maze_lines(w, h, rng) for _ in range(37)]
+        texts[3] = [" ".join(line) + "  " for line in texts[3]] + ["", "   "]       # whitespace is stripped
+        row = list(texts[5][0]); row[0] = 'L'; row[-1] = 'x'; texts[5][0] = "".join(row)     # lava + a second start
+        dev = EnvLevels.from_text(texts)
+        host = EnvLevels.from_levels([parse_level_text(orc.strip_level_lines(t)) for t in texts])
+        for name in ("wall", "goal", "lava", "start"):
+            assert torch.equal(getattr(dev, name).reshape(-1), getattr(host, name).reshape(-1)), name
+        want_starts = [sum(line.count('x') for line in t) for t in texts]
+        assert dev.n_starts.cpu().tolist() == want_starts
+    one = "\n".join(orc.strip_level_lines(golden_levels["maze_21x21"]))
+    assert torch.equal(EnvLevels.from_text([one]).wall.reshape(-1),
+                       EnvLevels.from_levels([parse_level_text(orc.strip_level_lines(golden_levels["maze_21x21"]))])
+                       .wall.reshape(-1))
+    good = ["xo", "oG"]
+    for bad, msg in ((["xo", "oT"], 'Invalid Character "T"'), (["oo", "oG"], "No starting states"),
+                     (["xo", "oo"], "No terminal goal states"), (["xo", "o"], "not a rectangle"),
+                     (["x?", "oo"], 'Invalid Character "?"')):
+        with pytest.raises(ValueError) as e1:
+            EnvLevels.from_text([good, bad, good])
+        assert msg in str(e1.value)
+        if len(bad[1]) == 2:
+            with pytest.raises(ValueError) as e2:
+                orc.parse_level_text(bad)
+            assert str(e1.value) == str(e2.value)
+    with pytest.raises(ValueError):
+        EnvLevels.from_text([good, ["xoo", "ooG"]])
+    # the packed batch drives the rollout kernel like any other per-env batch
+    from griduniverse_b200.envs import GridUniverseVecEnv
+    texts = [random_maze_lines(8, 8, rng) for _ in range(64)]
+    env = GridUniverseVecEnv(64, levels=EnvLevels.from_text(texts), auto_reset=True)
+    env.reset()
+    actions = np.random.RandomState(2).randint(0, 4, (50, 64)).astype(np.int32)
+    out = env.rollout(actions)
+    olv = [orc.parse_level_text(t) for t in texts]
+    _, er, ed, ep = orc.rollout(olv, [lv.starts[0] for lv in olv], actions, auto_reset=True)
+    assert np.array_equal(np.asarray(out["pos"]), ep)
+    assert np.array_equal(np.asarray(out["env_return"]), er.sum(axis=0))

@@ -45,4 +45,14 @@ if what in ("all", "env"):
             shape, n, T, env.levels.tables is not None, ms, n * T / ms * 1e3, 4.0 * n * T / ms / 1e6))
         ms = timeit(lambda: env.step(acts[0]), n=20)
         print("step    %s n=%d: %.3f ms  %.3e steps/s  %.0f GB/s alg(17B)" % (shape, n, ms, n / ms * 1e3, 17.0 * n / ms / 1e6))
+        from griduniverse_b200 import _cabi
+        obs = torch.empty(n, dtype=torch.int32, device="cuda"); rew = torch.empty_like(obs)
+        dn = torch.empty(n, dtype=torch.uint8, device="cuda")
+        L = _cabi.lib()
+        def raw(with_stats=True):
+            L.gu_step(env.levels.ref(), n, _cabi.ptr(acts[1]), _cabi.ptr(env.pos), _cabi.ptr(obs), _cabi.ptr(rew),
+                      _cabi.ptr(dn), None, _cabi.ptr(env.stats) if with_stats else None, 1, _cabi.stream_ptr())
+        for ws in (True, False):
+            ms = timeit(lambda: raw(ws), n=50)
+            print("gu_step %s n=%d stats=%s: %.3f ms  %.3e steps/s  %.0f GB/s alg(29B)" % (shape, n, ws, ms, n / ms * 1e3, 29.0 * n / ms / 1e6))
         del acts, env, lv
