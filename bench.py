@@ -384,7 +384,7 @@ def run_ours(args):
 
 def run_profile(args):
     """Short run for ncu (never a bench number): 2 rollout passes of the cfg-4 shape, a few sweeps
-    of each kind and one greedy extraction on the cfg-5 grid."""
+    of each kind, one greedy extraction and eight breadth-first levels on the cfg-5 grid."""
     import torch
     from griduniverse_b200 import synth
     from griduniverse_b200.envs import GridUniverseVecEnv
@@ -410,6 +410,9 @@ def run_profile(args):
             pl.sweep(b if i % 2 == 0 else a, a if i % 2 == 0 else b, 3, None, VI_GAMMA, res[i + 1:i + 2])
         tie = pl.greedy(a, VI_GAMMA)
         pl.sweep(a, b, 1, tie, VI_GAMMA)
+        if dt == np.float32:                 # eight levels of the shortest-path wavefront
+            from griduniverse_b200.paths import ShortestPaths
+            ShortestPaths(grid, chunk=8).solve(None, lava_blocks=True, max_levels=8)
         del a, b, tie, pl, grid
     torch.cuda.synchronize()
     print("profile run done")

@@ -89,8 +89,14 @@ constexpr int kBulkWarps = GU_ROLLOUT_WARPS;    // warps per block of the TMA ro
 // Per step: allowed = bit a of the current cell's info byte, the landing cell is
 // pos + allowed * delta[a] (delta = -X, +1, +X, -1 from a byte LUT), then one shared load fetches
 // the landing cell's info byte, whose goal / lava bits give reward and done (griduniverse_env.py:155).
-constexpr int kInfoRows = 8;       // action rows (time steps) per TMA box
-constexpr int kInfoStages = 2;
+#ifndef GU_INFO8_ROWS
+#define GU_INFO8_ROWS 8
+#endif
+#ifndef GU_INFO8_STAGES
+#define GU_INFO8_STAGES 2
+#endif
+constexpr int kInfoRows = GU_INFO8_ROWS;       // action rows (time steps) per TMA box
+constexpr int kInfoStages = GU_INFO8_STAGES;
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;

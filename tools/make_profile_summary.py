@@ -52,7 +52,11 @@ with open(os.path.join(ROOT, "profiles", tag + "_ncu_summary.txt"), "w") as f:
             traffic["sweep_greedy_f32_cfg5"] = rd + wr
         if "sweep_tiled_kernel<double, 3, 0" in r[ik]:
             traffic["sweep_greedy_f64_cfg5"] = rd + wr
-with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+tpath = os.path.join(ROOT, "profiles", "traffic.json")
+if os.path.exists(tpath):            # keep keys of kernels this capture did not reach (-c limit)
+    with open(tpath) as f:
+        traffic = dict(json.load(f), **traffic)
+with open(tpath, "w") as f:
     json.dump(traffic, f, indent=1)
 # launch list: keep kernel name, grid, block, time
 src = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
