@@ -159,18 +159,59 @@ __device__ __forceinline__ uint32_t info_of(const uint32_t* info, int j) {
   return (info[j >> 2] >> (8 * (j & 3))) & 0xffu;
 }
 
+// Byte offset of cell j's {reward, poison} entry: the goal / lava bits of all four cells of an
+// info word are masked at once and one PRMT per cell moves the byte into place (instead of a
+// shift and a mask per cell).  f32 entries are 8 bytes (bits 3-4 as they are), f64 entries 16.
+#ifndef GU_LUT_PRMT
+#define GU_LUT_PRMT 1
+#endif
+template <typename T>
+__device__ __forceinline__ uint32_t lut_offset(const uint32_t* info, int j) {
+#if GU_LUT_PRMT
+  const uint32_t m = sizeof(T) == 4 ? (info[j >> 2] & 0x18181818u) : ((info[j >> 2] << 1) & 0x30303030u);
+  return (j & 3) == 0 ? (m & 0xffu) : __byte_perm(m, 0u, 0x4440u + (j & 3));
+#else
+  const uint32_t inf = (info[j >> 2] >> (8 * (j & 3))) & 0xffu;
+  return sizeof(T) == 4 ? (inf & 0x18u) : ((inf & 0x18u) << 1);
+#endif
+}
+template <typename T>
+__device__ __forceinline__ T reward_at(const Luts<T>& l, uint32_t off) {
+  return *reinterpret_cast<const T*>(reinterpret_cast<const char*>(&l.reward[0][0]) + off);
+}
+__device__ __forceinline__ float2 reward_poison_at(const Luts<float>& l, uint32_t off) {
+  return *reinterpret_cast<const float2*>(reinterpret_cast<const char*>(&l.reward[0][0]) + off);
+}
+__device__ __forceinline__ double2 reward_poison_at(const Luts<double>& l, uint32_t off) {
+  return *reinterpret_cast<const double2*>(reinterpret_cast<const char*>(&l.reward[0][0]) + off);
+}
+
 // rint(t) for t = q * 1e8.  f32: |t| >= 2^23 is already integral (the common case: |q| > 0.084).
 // f64: the magic-number add is exact below 2^51.  `need_slow` collects the rare other cases.
+#ifndef GU_F32_FRND
+#define GU_F32_FRND 1
+#endif
 __device__ __forceinline__ float round_fast(float t, float& worst) {
+#if GU_F32_FRND
+  return rintf(t);                          // FRND on the otherwise idle XU pipe; no slow path needed
+#else
   worst = fminf(worst, fabsf(t));           // slow path if any |t| < 2^23
   return t;
+#endif
 }
+#ifndef GU_F64_FRND
+#define GU_F64_FRND 1
+#endif
 __device__ __forceinline__ double round_fast(double t, double& worst) {
+#if GU_F64_FRND
+  return rint(t);                           // FRND.F64
+#else
   worst = max_nn(worst, fabs(t));           // slow path if any |t| >= 2^51
   return __dadd_rn(__dadd_rn(t, 6755399441055744.0), -6755399441055744.0);
+#endif
 }
-__device__ __forceinline__ bool round_needs_slow(float worst) { return worst < 8388608.0f; }
-__device__ __forceinline__ bool round_needs_slow(double worst) { return !(worst < 2251799813685248.0); }
+__device__ __forceinline__ bool round_needs_slow(float worst) { return GU_F32_FRND ? false : worst < 8388608.0f; }
+__device__ __forceinline__ bool round_needs_slow(double worst) { return GU_F64_FRND ? false : !(worst < 2251799813685248.0); }
 __device__ __forceinline__ float round_worst_init(float) { return CUDART_INF_F; }
 __device__ __forceinline__ double round_worst_init(double) { return 0.0; }
 
@@ -313,7 +354,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     for (int j = 0; j < CPT; ++j) {
       r.g[j] = N::mul(gamma, r.v[j]);
       if constexpr (TIES)
-        r.rt[j] = round_fast(N::mul(N::add(reward_lut(luts, info_of(r.info, j)), r.g[j]), N::scale()), worst);
+        r.rt[j] = round_fast(N::mul(N::add(reward_at(luts, lut_offset<T>(r.info, j)), r.g[j]), N::scale()), worst);
     }
     const T hg = N::mul(gamma, r.hv);
     if constexpr (TIES) {
@@ -321,7 +362,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
       if (round_needs_slow(worst)) {   // rare: re-round everything with rint() (idempotent on integers)
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-          r.rt[j] = N::rnd(N::mul(N::add(reward_lut(luts, info_of(r.info, j)), r.g[j]), N::scale()));
+          r.rt[j] = N::rnd(N::mul(N::add(reward_at(luts, lut_offset<T>(r.info, j)), r.g[j]), N::scale()));
         ht = N::rnd(N::mul(N::add(reward_lut(luts, r.hinfo), hg), N::scale()));
       }
     }
@@ -382,7 +423,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             ga[1] = (inf & kBlkR) ? gs : (c == CPT - 1 ? cur.gr : cur.g[c + 1 < CPT ? c + 1 : c]);
             ga[2] = (inf & kBlkD) ? gs : dn.g[c];
             ga[3] = (inf & kBlkL) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
-            const auto rp = reward_poison_lut(luts, inf);   // {R[s], NaN if s terminal else 0}
+            const auto rp = reward_poison_at(luts, lut_offset<T>(cur.info, c));   // {R[s], NaN if s terminal else 0}
             const T rs = rp.x;
             T ra[4], m = T(0);
             if constexpr (TIES) {
