@@ -75,50 +75,63 @@ bfs_expand_kernel(GridView g, const uint32_t* __restrict__ vin, uint32_t* __rest
   const int lane = threadIdx.x & 31;
   const int rows = g.row_end - g.row_begin;
   const int ar0 = 1 + blockIdx.y * kBfsRows;                    // first array row of this thread
-  const int ar1 = min(ar0 + kBfsRows, rows + 1);
   const int pw = g.pitch_words, nq = pw >> 2;
   const bool in = q < nq;
+  const bool edge_l = in && lane == 0 && q > 0, edge_r = lane == 31 && q + 1 < nq;
   const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-  auto quad = [&](int ar) -> uint4 {                            // ghost rows hold zeros
-    return reinterpret_cast<const uint4*>(vin + static_cast<size_t>(ar) * pw)[q];
-  };
-  uint4 up = in ? quad(ar0 - 1) : zero;
-  uint4 cur = in ? quad(ar0) : zero;
+  // running pointers: row ar of the input plane (quad view / word view), output plane, distances
+  const uint32_t* pin = vin + static_cast<size_t>(ar0) * pw + 4 * q;
+  uint32_t* pout = vout + static_cast<size_t>(ar0) * pw + 4 * q;
+  int32_t* pd = dist + static_cast<size_t>(ar0) * g.pitch + (q << 7);
+  const uint32_t* pwall = g.wall + static_cast<size_t>(ar0) * pw + 4 * q;
+  const uint32_t* plava = g.lava + static_cast<size_t>(ar0) * pw + 4 * q;
+  uint4 up = in ? *reinterpret_cast<const uint4*>(pin - pw) : zero;   // ghost rows hold zeros
+  uint4 cur = in ? *reinterpret_cast<const uint4*>(pin) : zero;
   unsigned fresh = 0;
-  for (int ar = ar0; ar < ar1; ++ar) {
-    const uint4 dn = in ? quad(ar + 1) : zero;
-    uint32_t lw = __shfl_up_sync(0xffffffffu, cur.w, 1);
-    uint32_t rw = __shfl_down_sync(0xffffffffu, cur.x, 1);
-    if (lane == 0) lw = (in && q > 0) ? vin[static_cast<size_t>(ar) * pw + 4 * q - 1] : 0u;
-    if (lane == 31) rw = (q + 1 < nq) ? vin[static_cast<size_t>(ar) * pw + 4 * q + 4] : 0u;
-    if (in) {
-      const size_t idx = static_cast<size_t>(ar) * pw + 4 * q;
-      uint32_t nw[4];
-      nw[0] = (up.x | dn.x | (cur.x << 1) | (lw >> 31) | (cur.x >> 1) | (cur.y << 31)) & ~cur.x;
-      nw[1] = (up.y | dn.y | (cur.y << 1) | (cur.x >> 31) | (cur.y >> 1) | (cur.z << 31)) & ~cur.y;
-      nw[2] = (up.z | dn.z | (cur.z << 1) | (cur.y >> 31) | (cur.z >> 1) | (cur.w << 31)) & ~cur.z;
-      nw[3] = (up.w | dn.w | (cur.w << 1) | (cur.z >> 31) | (cur.w >> 1) | (rw << 31)) & ~cur.w;
-      if (nw[0] | nw[1] | nw[2] | nw[3]) {                      // candidates: now look at the masks
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          if (nw[k]) nw[k] &= open_word(g, idx + k, 4 * q + k, lava_blocks);
-          uint32_t m = nw[k];
-          if (m) {
-            fresh += __popc(m);
-            int32_t* d = dist + static_cast<size_t>(ar) * g.pitch + ((4 * q + k) << 5);
-            do {
-              const int b = __ffs(m) - 1;
-              m &= m - 1;
-              d[b] = level;
-            } while (m);
+  for (int k = 0; k < kBfsRows; ++k) {
+    if (ar0 + k <= rows) {                                       // uniform across the block
+      const uint4 dn = in ? *reinterpret_cast<const uint4*>(pin + pw) : zero;
+      uint32_t lw = __shfl_up_sync(0xffffffffu, cur.w, 1);
+      uint32_t rw = __shfl_down_sync(0xffffffffu, cur.x, 1);
+      if (lane == 0) lw = edge_l ? pin[-1] : 0u;
+      if (lane == 31) rw = edge_r ? pin[4] : 0u;
+      if (in) {
+        uint32_t nw[4];
+        nw[0] = (up.x | dn.x | (cur.x << 1) | (lw >> 31) | (cur.x >> 1) | (cur.y << 31)) & ~cur.x;
+        nw[1] = (up.y | dn.y | (cur.y << 1) | (cur.x >> 31) | (cur.y >> 1) | (cur.z << 31)) & ~cur.y;
+        nw[2] = (up.z | dn.z | (cur.z << 1) | (cur.y >> 31) | (cur.z >> 1) | (cur.w << 31)) & ~cur.z;
+        nw[3] = (up.w | dn.w | (cur.w << 1) | (cur.z >> 31) | (cur.w >> 1) | (rw << 31)) & ~cur.w;
+        if (nw[0] | nw[1] | nw[2] | nw[3]) {                    // candidates: now look at the masks
+          const uint4 wl = *reinterpret_cast<const uint4*>(pwall);
+          uint4 bl = wl;
+          if (lava_blocks) {
+            const uint4 lv = *reinterpret_cast<const uint4*>(plava);
+            bl = make_uint4(wl.x | lv.x, wl.y | lv.y, wl.z | lv.z, wl.w | lv.w);
+          }
+          const uint32_t blocked[4] = {bl.x, bl.y, bl.z, bl.w};
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t m = nw[c] & ~blocked[c] & column_mask(g, 4 * q + c);
+            nw[c] = m;
+            if (m) {
+              fresh += __popc(m);
+              int32_t* d = pd + (c << 5);
+              do {
+                const int b = __ffs(m) - 1;
+                m &= m - 1;
+                d[b] = level;
+              } while (m);
+            }
           }
         }
+        *reinterpret_cast<uint4*>(pout) = make_uint4(cur.x | nw[0], cur.y | nw[1], cur.z | nw[2], cur.w | nw[3]);
       }
-      reinterpret_cast<uint4*>(vout + static_cast<size_t>(ar) * pw)[q] =
-          make_uint4(cur.x | nw[0], cur.y | nw[1], cur.z | nw[2], cur.w | nw[3]);
+      up = cur;
+      cur = dn;
+      pin += pw; pout += pw; pwall += pw; plava += pw;
+      pd += g.pitch;
     }
-    up = cur;
-    cur = dn;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) fresh += __shfl_xor_sync(0xffffffffu, fresh, o);
