@@ -65,3 +65,49 @@ extern "C" __attribute__((visibility("default"))) int gu_pack_level_text(
   GU_CHECK_LAUNCH();
   return GU_OK;
 }
+
+// ---- batched ASCII render (griduniverse_env.py:202-221) --------------------------------------
+// One thread per (env, cell): the cell's glyph with precedence x < G < L < # followed by a blank,
+// a newline after the last column of a row, and one more newline closing the frame.
+namespace gu {
+
+__global__ void __launch_bounds__(256)
+render_ansi_kernel(const uint32_t* __restrict__ wall, const uint32_t* __restrict__ goal,
+                   const uint32_t* __restrict__ lava, int per_env, long long n, int X, int cells,
+                   const int32_t* __restrict__ pos, uint8_t* __restrict__ text, long long frame) {
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * cells) return;
+  const long long env = i / cells;
+  const int c = static_cast<int>(i - env * cells);
+  const size_t w = per_env ? static_cast<size_t>(c >> 5) * n + env : (c >> 5);
+  const uint32_t bit = 1u << (c & 31);
+  uint8_t ch = 'o';
+  if (pos[env] == c) ch = 'x';
+  if (goal[w] & bit) ch = 'G';
+  if (lava[w] & bit) ch = 'L';
+  if (wall[w] & bit) ch = '#';
+  const int y = c / X, x = c - y * X;
+  uint8_t* out = text + env * frame + static_cast<size_t>(y) * (2 * X + 1) + 2 * x;
+  out[0] = ch;
+  out[1] = ' ';
+  if (x == X - 1) out[2] = '\n';
+  if (c == cells - 1) out[3] = '\n';
+}
+
+}  // namespace gu
+
+extern "C" __attribute__((visibility("default"))) int gu_render_ansi(
+    const gu_levels* lv, int64_t n, const int32_t* pos, uint8_t* text, void* stream) {
+  if (!lv || !lv->wall || !lv->goal || !lv->lava) return GU_ERR_NULL;
+  if (n == 0) return GU_OK;
+  if (!pos || !text) return GU_ERR_NULL;
+  if (lv->X <= 0 || lv->Y <= 0 || n < 0 || static_cast<int64_t>(lv->X) * lv->Y > (1 << 24)) return GU_ERR_SHAPE;
+  const int cells = lv->X * lv->Y;
+  const long long frame = static_cast<long long>(lv->Y) * (2 * lv->X + 1) + 1;
+  const long long blocks = (n * cells + 255) / 256;
+  if (blocks > 2147483647LL) return GU_ERR_SHAPE;
+  render_ansi_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lv->wall, lv->goal, lv->lava, lv->per_env, n, lv->X, cells, pos, text, frame);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

@@ -179,6 +179,18 @@ class GridUniverseVecEnv(object):
         torch.cuda.current_stream().synchronize()
         return {k: (None if v is None else v.numpy().copy()) for k, v in res.items()}
 
+    def render_ansi(self, envs=None):
+        """render(mode='ansi') of the whole batch in one launch (griduniverse_env.py:202-221):
+        a list of strings, one frame per env (or for the given env indices only)."""
+        n = self.num_envs
+        frame = self.y_max * (2 * self.x_max + 1) + 1
+        text = torch.empty((n, frame), dtype=torch.uint8, device=self.device)
+        rc = self._lib.gu_render_ansi(self.levels.ref(), n, _cabi.ptr(self.pos), _cabi.ptr(text), _cabi.stream_ptr())
+        _cabi.check("gu_render_ansi", rc)
+        if envs is not None:
+            text = text[torch.as_tensor(list(envs), device=self.device, dtype=torch.long)]
+        return [bytes(row).decode("ascii") for row in text.cpu().numpy()]
+
     def rollout_stream(self, slabs):
         """Streamed rollout from HOST memory: ``slabs`` is an iterable of pinned int32 host
         tensors [t_i, N] (consecutive time slices of the action stream).  Each slab is copied

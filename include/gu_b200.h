@@ -148,6 +148,11 @@ int gu_pack_level_text(const uint8_t* text, int64_t n_levels, int32_t X, int32_t
                        uint32_t* goal, uint32_t* lava, int32_t* start, int32_t* n_starts,
                        int32_t* status, void* stream);
 
+/* Batched render(mode='ansi') (griduniverse_env.py:202-221): for each env the Y text rows of
+ * "<glyph><blank>" pairs plus '\n', then one closing '\n'; glyph precedence x (agent at pos[env])
+ * < G < L < #.  `text`: uint8[n][Y*(2X+1)+1]. */
+int gu_render_ansi(const gu_levels* lv, int64_t n, const int32_t* pos, uint8_t* text, void* stream);
+
 /* ---- whole-grid planning ------------------------------------------------ */
 
 /* One grid, or one row shard of it, for the sweep / greedy kernels.

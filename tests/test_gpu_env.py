@@ -274,3 +274,25 @@ def test_batched_level_text_packing(golden_levels):
     _, er, ed, ep = orc.rollout(olv, [lv.starts[0] for lv in olv], actions, auto_reset=True)
     assert np.array_equal(np.asarray(out["pos"]), ep)
     assert np.array_equal(np.asarray(out["env_return"]), er.sum(axis=0))
+
+
+def test_batched_ansi_render(golden_cases, golden_levels):
+    """gu_render_ansi against the oracle's render (itself pinned to the reference's ansi goldens)."""
+    X, Y, n = 7, 5, 96
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, seed=4)
+    levels = [Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    olevels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    env = GridUniverseVecEnv(n, levels=levels, auto_reset=False)
+    env.reset()
+    env.step(np.random.RandomState(0).randint(0, 4, n).astype(np.int32))
+    frames = env.render_ansi()
+    pos = env.pos.cpu().numpy()
+    assert frames == [orc.render_ansi(olevels[i], int(pos[i])) for i in range(n)]
+    assert env.render_ansi(envs=[5, 2]) == [frames[5], frames[2]]
+    for p in golden_cases["probes"]:                       # shared level: the reference's own frames
+        if p["name"] == "render_ansi_test_env":
+            from griduniverse_b200.level import parse_level_text
+            lvl = parse_level_text(orc.strip_level_lines(golden_levels[p["level"]]))
+            shared = GridUniverseVecEnv(3, levels=EnvLevels.shared(lvl), auto_reset=False)
+            shared.reset(start_states=[p["state"]] * 3)
+            assert shared.render_ansi() == [p["ansi"]] * 3
