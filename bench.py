@@ -148,7 +148,7 @@ def run_reference(args):
                                 "sample": "%d replicas of a 512x512 synthetic maze, 4 sweep+greedy iterations "
                                           "each, fp32 oracle" % procs}},
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def env_config(n_gpus):
@@ -377,7 +377,7 @@ def run_ours(args):
             },
             "cfg3": cfg3,
         }
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -418,6 +418,19 @@ def run_profile(args):
     print("profile run done")
 
 
+_RESULT_FD = None
+
+
+def emit(line):
+    """The one JSON line of the run, on the real stdout."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
@@ -430,6 +443,12 @@ def main():
     ap.add_argument("--profile", action="store_true", help="short kernel sequence for ncu")
     ap.add_argument("--profile-div", type=int, default=1, help="shrink the profile workloads by this factor")
     args = ap.parse_args()
+    # stdout carries exactly one line, the JSON result: everything else that writes to fd 1
+    # (NCCL prints its version banner there) is sent to stderr
+    global _RESULT_FD
+    sys.stdout.flush()
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     if args.profile:
         run_profile(args)
     elif args.impl == "reference":
