@@ -60,7 +60,7 @@ step_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restr
 // requests and does the step on 64-bit masks in registers.  Same bytes, no dependent chain.
 template <int WORDS>
 __global__ void __launch_bounds__(256)
-step_small_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
+step_small_kernel(LevelsView lv, const int32_t* __restrict__ actions, const int32_t* pos_in, int32_t* pos,
                   int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
                   const int32_t* __restrict__ start_choice, int64_t* stats, uint32_t flags) {
   const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * 4;
@@ -69,7 +69,7 @@ step_small_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* _
   long long rsum = 0, dcnt = 0;
   if (i0 < lv.N) {
     const int4 av = *reinterpret_cast<const int4*>(actions + i0);
-    const int4 sv = *reinterpret_cast<const int4*>(pos + i0);
+    const int4 sv = *reinterpret_cast<const int4*>(pos_in + i0);
     uint4 pw[WORDS], pg[WORDS], pl[WORDS];
 #pragma unroll
     for (int k = 0; k < WORDS; ++k) {
@@ -102,7 +102,7 @@ step_small_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* _
       rsum += r[e];
       dcnt += d[e] ? 1 : 0;
     }
-    *reinterpret_cast<int4*>(pos + i0) = make_int4(nxt[0], nxt[1], nxt[2], nxt[3]);
+    if (pos) *reinterpret_cast<int4*>(pos + i0) = make_int4(nxt[0], nxt[1], nxt[2], nxt[3]);   // NULL: look_step_ahead
     if (obs) *reinterpret_cast<int4*>(obs + i0) = make_int4(n[0], n[1], n[2], n[3]);
     if (reward) *reinterpret_cast<int4*>(reward + i0) = make_int4(r[0], r[1], r[2], r[3]);
     if (done) *reinterpret_cast<uchar4*>(done + i0) = make_uchar4(d[0], d[1], d[2], d[3]);
@@ -218,9 +218,9 @@ extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* l
   if (small) {
     const unsigned blocks = static_cast<unsigned>((n / 4 + 255) / 256);
     if (lv->words == 1)
-      step_small_kernel<1><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
+      step_small_kernel<1><<<blocks, 256, 0, st>>>(v, actions, pos, pos, obs, reward, done, start_choice, stats, flags);
     else
-      step_small_kernel<2><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
+      step_small_kernel<2><<<blocks, 256, 0, st>>>(v, actions, pos, pos, obs, reward, done, start_choice, stats, flags);
   } else if (vec) {
     const int64_t threads = n / 4;
     step_kernel<4><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
@@ -277,6 +277,21 @@ extern "C" __attribute__((visibility("default"))) int gu_look_step_ahead(const g
   if (rc) return rc;
   if (!states || !actions) return GU_ERR_NULL;
   if (m == 0) return GU_OK;
+  if (flags & ~static_cast<uint32_t>(GU_FLAG_NO_CARE_TERMINAL)) return GU_ERR_MODE;
+  const bool small = lv->per_env && lv->words <= 2 && m % 4 == 0 && aligned16(lv->wall) && aligned16(lv->goal) &&
+                     aligned16(lv->lava) && aligned16(states) && aligned16(actions) && (!next || aligned16(next)) &&
+                     (!reward || aligned16(reward)) && (!terminal || aligned4(terminal));
+  if (small) {   // pair i is looked up in env i's level: the one-step kernel without the position update
+    const unsigned blocks = static_cast<unsigned>((m / 4 + 255) / 256);
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const LevelsView v = view_of(lv, m);
+    if (lv->words == 1)
+      step_small_kernel<1><<<blocks, 256, 0, st>>>(v, actions, states, nullptr, next, reward, terminal, nullptr, nullptr, flags);
+    else
+      step_small_kernel<2><<<blocks, 256, 0, st>>>(v, actions, states, nullptr, next, reward, terminal, nullptr, nullptr, flags);
+    GU_CHECK_LAUNCH();
+    return GU_OK;
+  }
   look_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       view_of(lv, m), m, states, actions, next, reward, terminal, flags);
   GU_CHECK_LAUNCH();

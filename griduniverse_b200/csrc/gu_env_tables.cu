@@ -348,7 +348,6 @@ rollout_nt16_kernel(int64_t N, int64_t T, int cells, const uint16_t* __restrict_
 }
 
 static inline bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-static inline bool al4(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 3u) == 0; }
 
 int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
                    int32_t* reward, uint8_t* done, const int32_t* start_choice, int32_t* env_return,

@@ -265,6 +265,10 @@ __device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot, bool
 template <typename T>
 __global__ void peer_wait_kernel(PeerArgs<T> p) { (void)peer_wait_slot(p, p.slot); }
 
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+
 template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false>
 __global__ void __launch_bounds__(kTiledWarps * 32)
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
@@ -279,6 +283,14 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   constexpr bool TIES = (KIND == GU_POLICY_GREEDY) || WRITE_TIE;
   __shared__ T scratch[kTiledWarps];
   __shared__ __align__(16) Luts<T> luts;
+  // GU_POLICY_PROBS: a thread's CPT cells own CPT*4 probabilities = UPT 16-byte units that sit 128
+  // bytes apart from the next lane's, so a direct load touches 32 lines per request.  Instead the
+  // warp copies its strip of the [cells][4] row with coalesced 16-byte cp.async requests (unit
+  // k*32+lane per request) into a double-buffered shared stage, padded by one unit per thread chunk
+  // so the per-thread reads are bank-conflict free, one row ahead of the compute.
+  constexpr int UPT = CPT * static_cast<int>(sizeof(T)) / 4;
+  constexpr int kStage = 32 * UPT + 32;
+  __shared__ __align__(16) uint4 pstage[KIND == GU_POLICY_PROBS ? kTiledWarps * 2 * kStage : 1];
   if (!PEER) {
     if (gate != nullptr && *gate < gate_thr) return;
   } else if (peer.slot > 0) {
@@ -378,6 +390,24 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     }
   };
 
+  auto issue_policy = [&](int ry, int buf) {
+    if constexpr (KIND == GU_POLICY_PROBS) {
+      if (ry < ry1) {
+        const char* src = static_cast<const char*>(policy) +
+                          (static_cast<size_t>(ry + 1) * pitch + wx0) * (4 * sizeof(T));
+        const uint32_t dst = smem_u32(&pstage[((threadIdx.x >> 5) * 2 + buf) * kStage]);
+        const int strip_units = min(g.pitch - wx0, 32 * CPT) * static_cast<int>(sizeof(T)) / 4;
+#pragma unroll
+        for (int k = 0; k < UPT; ++k) {
+          const int u = k * 32 + lane;
+          if (u < strip_units) cp_async16(dst + (u + u / UPT) * 16, src + static_cast<size_t>(u) * 16);
+        }
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+  };
+  issue_policy(ry0, 0);
+
   T dmax = N::neg_inf();
   const int last_ar = rows + 1;                 // bottom ghost row of the shard's arrays
   issue_loads(ry0, w[0]);                       // array row ry0     = row above the first owned row
@@ -398,6 +428,12 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
         // the row after that goes into the raw fields of `up` (its v / info are dead, its g / rt
         // stay valid for this row's compute); the loads are in flight while this row is computed
         issue_loads(min(ry + 3, last_ar), up);
+        if constexpr (KIND == GU_POLICY_PROBS) {
+          __syncwarp();                                  // everyone is done reading the other buffer
+          issue_policy(ry + 1, (ry + 1 - ry0) & 1);
+          asm volatile("cp.async.wait_group 1;" ::: "memory");
+          __syncwarp();                                  // this row's units from all lanes have landed
+        }
         if (active) {
           const size_t o = static_cast<size_t>(ry + 1) * pitch + x0;
           T out[CPT];
@@ -442,7 +478,16 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             } else if constexpr (KIND == GU_POLICY_GREEDY) {
               out[c] = backup_ties(rs, ra, m, ga, luts);
             } else if constexpr (KIND == GU_POLICY_PROBS) {
-              const T* pp = static_cast<const T*>(policy) + (o + c) * 4;
+              const uint4* mine = &pstage[((threadIdx.x >> 5) * 2 + ((ry - ry0) & 1)) * kStage + lane * (UPT + 1)];
+              T pp[4];
+              if constexpr (sizeof(T) == 4) {
+                const float4 f = *reinterpret_cast<const float4*>(mine + c);
+                pp[0] = f.x; pp[1] = f.y; pp[2] = f.z; pp[3] = f.w;
+              } else {
+                const double2 d0 = *reinterpret_cast<const double2*>(mine + 2 * c);
+                const double2 d1 = *reinterpret_cast<const double2*>(mine + 2 * c + 1);
+                pp[0] = d0.x; pp[1] = d0.y; pp[2] = d1.x; pp[3] = d1.y;
+              }
               T acc = rs;
 #pragma unroll
               for (int a = 0; a < 4; ++a) acc = N::add(acc, N::mul(pp[a], ga[a]));
@@ -688,6 +733,7 @@ int sweep_tiled_f32(const gu_grid* g, const float* vin, float* vout, int kind, c
 int sweep_tiled_f64(const gu_grid* g, const double* vin, double* vout, int kind, const void* policy, double gamma,
                     double* residual, const double* gate, double gate_thr, cudaStream_t st) {
   if (!tiled_ok(g, sizeof(double), vin, vout)) return GU_ERR_UNSUPPORTED;
+  if (kind == GU_POLICY_PROBS && (reinterpret_cast<uintptr_t>(policy) & 15u)) return GU_ERR_UNSUPPORTED;
   return launch_tiled<double, false>(g, vin, vout, nullptr, kind, policy, gamma, residual, gate, gate_thr, st);
 }
 int greedy_tiled_f32(const gu_grid* g, const float* v, uint8_t* tie, float gamma, cudaStream_t st) {
@@ -708,6 +754,7 @@ extern "C" __attribute__((visibility("default"))) int gu_sweep_peer_f32(
     float* residual, const gu_peer_links* peer, void* stream) {
   if (!g || !v_in || !v_out) return GU_ERR_NULL;
   if (!tiled_ok(g, sizeof(float), v_in, v_out)) return GU_ERR_UNSUPPORTED;
+  if (policy_kind == GU_POLICY_PROBS && (!policy || (reinterpret_cast<uintptr_t>(policy) & 15u))) return GU_ERR_ALIGN;
   return launch_tiled_peer<float>(g, v_in, v_out, policy_kind, policy, gamma, residual, peer,
                                   static_cast<cudaStream_t>(stream));
 }
@@ -717,6 +764,7 @@ extern "C" __attribute__((visibility("default"))) int gu_sweep_peer_f64(
     double* residual, const gu_peer_links* peer, void* stream) {
   if (!g || !v_in || !v_out) return GU_ERR_NULL;
   if (!tiled_ok(g, sizeof(double), v_in, v_out)) return GU_ERR_UNSUPPORTED;
+  if (policy_kind == GU_POLICY_PROBS && (!policy || (reinterpret_cast<uintptr_t>(policy) & 15u))) return GU_ERR_ALIGN;
   return launch_tiled_peer<double>(g, v_in, v_out, policy_kind, policy, gamma, residual, peer,
                                    static_cast<cudaStream_t>(stream));
 }

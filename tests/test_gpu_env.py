@@ -296,3 +296,22 @@ def test_batched_ansi_render(golden_cases, golden_levels):
             shared = GridUniverseVecEnv(3, levels=EnvLevels.shared(lvl), auto_reset=False)
             shared.reset(start_states=[p["state"]] * 3)
             assert shared.render_ansi() == [p["ansi"]] * 3
+
+
+@pytest.mark.parametrize("shape,n", [((8, 8), 1024), ((8, 8), 1001), ((5, 6), 64), ((16, 16), 256)])
+def test_look_step_ahead_per_env_levels(shape, n):
+    """look_step_ahead for pair i on env i's own level (both kernels: 64-bit-mask and generic)."""
+    X, Y = shape
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, seed=2)
+    levels = [Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    olevels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    env = GridUniverseVecEnv(n, levels=levels)
+    rs = np.random.RandomState(3)
+    states = rs.randint(0, X * Y, n).astype(np.int32)
+    actions = rs.randint(0, 4, n).astype(np.int32)
+    for care in (True, False):
+        nxt, rew, term = env.look_step_ahead(states, actions, care_about_terminal=care)
+        exp = [orc.look_step_ahead(olevels[i], int(states[i]), int(actions[i]), care) for i in range(n)]
+        assert np.array_equal(nxt, [e[0] for e in exp])
+        assert np.array_equal(rew, [e[1] for e in exp])
+        assert np.array_equal(np.asarray(term).astype(bool), [e[2] for e in exp])
