@@ -203,6 +203,120 @@ vi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ 
   }
 }
 
+// ---- whole policy_iteration loop (dynamic_programming.py:31-57) in one thread block ----------
+// Shared memory: three value arrays (current, scratch, last converged), the info bytes and the
+// tie masks of the current greedy policy.  The caller's policy (kind0) is evaluated until the
+// first improvement; from then on the policy is the tie masks held in shared memory.
+constexpr int64_t kPiSmallMaxCells = 8500;   // 3 x f64 + 2 bytes per cell within 227 KB
+
+__device__ __forceinline__ double block_max(double v, double* red, double* out) {
+  v = warp_max(v);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const double w = warp_max(red[threadIdx.x]);
+    if (threadIdx.x == 0) *out = w;
+  }
+  __syncthreads();
+  return *out;
+}
+
+__global__ void __launch_bounds__(kSmallThreads, 1)
+pi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ vout,
+                uint8_t* __restrict__ tie, int kind0, const void* __restrict__ policy, double gamma,
+                double threshold, int max_steps, int32_t* meta, double* last_delta_eval) {
+  extern __shared__ double smem_d[];
+  const int N = g.X * g.Y;
+  double* v = smem_d;               // current value function
+  double* scratch = smem_d + N;
+  double* last = smem_d + 2 * N;    // last converged value function (:36,45)
+  uint8_t* info = reinterpret_cast<uint8_t*>(smem_d + 3 * N);
+  uint8_t* pmask = info + N;
+  __shared__ double red[32];
+  __shared__ double red_out;
+  const int tid = threadIdx.x;
+
+  for (int s = tid; s < N; s += kSmallThreads) {
+    const int y = s / g.X, x = s - y * g.X;
+    CellIn<double> c;
+    gather_cell(g, v0, x, y, c);
+    const size_t w = static_cast<size_t>(y + 1) * g.pitch_words + (x >> 5);
+    const uint32_t goal = (g.goal[w] >> (x & 31)) & 1u, lava = (g.lava[w] >> (x & 31)) & 1u;
+    info[s] = static_cast<uint8_t>(c.blk | (goal << 4) | (lava << 5));
+    v[s] = c.vs;
+    last[s] = c.vs;
+  }
+  __syncthreads();
+
+  auto greedy_of = [&](const double* from) {             // utils.py:55-72 on `from` -> pmask
+    for (int s = tid; s < N; s += kSmallThreads) {
+      CellIn<double> c;
+      small_cell(from, info, s, g.X, c);
+      double gn[4];
+      discounted_next(c, gamma, gn);
+      pmask[s] = static_cast<uint8_t>(tie_mask_of(c, gn));
+    }
+    __syncthreads();
+  };
+
+  int sweeps = 0, improved = 0, exhausted = 0;
+  int kind = kind0;
+  double delta_eval = 0.0;
+  for (int step = 0; step < max_steps; ++step) {
+    double dmax = -CUDART_INF;
+    for (int s = tid; s < N; s += kSmallThreads) {
+      CellIn<double> c;
+      small_cell(v, info, s, g.X, c);
+      const int y = s / g.X, x = s - y * g.X;
+      const size_t cell = static_cast<size_t>(y + 1) * g.pitch + x;
+      double vnew;
+      if (improved) {
+        double gn[4];
+        discounted_next(c, gamma, gn);
+        vnew = backup_mask(c, gn, pmask[s]);
+      } else if (kind == GU_POLICY_PROBS) vnew = cell_update<double, GU_POLICY_PROBS>(c, gamma, policy, cell);
+      else if (kind == GU_POLICY_MASK) vnew = cell_update<double, GU_POLICY_MASK>(c, gamma, policy, cell);
+      else if (kind == GU_POLICY_UNIFORM) vnew = cell_update<double, GU_POLICY_UNIFORM>(c, gamma, policy, cell);
+      else vnew = cell_update<double, GU_POLICY_GREEDY>(c, gamma, policy, cell);
+      scratch[s] = vnew;
+      const double d = __dadd_rn(c.vs, -vnew);
+      dmax = d > dmax ? d : dmax;
+    }
+    delta_eval = block_max(dmax, red, &red_out);          // np.max(v - v_new), :40
+    { double* t = v; v = scratch; scratch = t; }
+    ++sweeps;
+    if (delta_eval < threshold) {                          // evaluation converged, :42
+      greedy_of(v);                                        // :43 (in place, utils.py:69)
+      improved = 1;
+      double lmax = -CUDART_INF;
+      for (int s = tid; s < N; s += kSmallThreads) {
+        const double d = __dadd_rn(last[s], -v[s]);
+        lmax = d > lmax ? d : lmax;
+        last[s] = v[s];
+      }
+      const double delta = block_max(lmax, red, &red_out); // np.max(last_converged - v_new), :44
+      if (delta < threshold) break;                        // :46-47
+    } else if (step == max_steps - 1) {                    // :48-54
+      greedy_of(last);
+      improved = 1;
+      exhausted = 1;
+    }
+  }
+
+  for (int s = tid; s < N; s += kSmallThreads) {
+    const int y = s / g.X, x = s - y * g.X;
+    const size_t cell = static_cast<size_t>(y + 1) * g.pitch + x;
+    vout[cell] = last[s];
+    if (improved) tie[cell] = pmask[s];
+  }
+  if (tid == 0) {
+    meta[0] = sweeps;
+    meta[1] = improved;
+    meta[2] = exhausted;
+    *last_delta_eval = delta_eval;
+  }
+}
+
 }  // namespace gu
 
 using namespace gu;
@@ -272,6 +386,26 @@ extern "C" __attribute__((visibility("default"))) int gu_vi_small_f64(const gu_g
   vi_small_kernel<<<1, kSmallThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       view_of(g), v0, v_out, tie_mask, policy_kind, policy, gamma, threshold, max_steps, sweeps_out,
       last_delta);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int64_t gu_pi_small_max_cells(void) { return kPiSmallMaxCells; }
+
+extern "C" __attribute__((visibility("default"))) int gu_pi_small_f64(
+    const gu_grid* g, const double* v0, double* v_out, uint8_t* tie_mask, int policy_kind, const void* policy,
+    double gamma, double threshold, int32_t max_steps, int32_t* meta, double* last_delta_eval, void* stream) {
+  if (!g || !v0 || !v_out || !tie_mask || !meta || !last_delta_eval) return GU_ERR_NULL;
+  if (policy_kind < GU_POLICY_PROBS || policy_kind > GU_POLICY_GREEDY) return GU_ERR_MODE;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  const int64_t N = static_cast<int64_t>(g->X) * g->Y;
+  if (g->row_begin != 0 || g->row_end != g->Y || N > kPiSmallMaxCells || max_steps < 0) return GU_ERR_SHAPE;
+  const size_t smem = static_cast<size_t>(N) * 26 + 16;
+  cudaError_t e = cudaFuncSetAttribute(pi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       static_cast<int>(smem));
+  if (e != cudaSuccess) return static_cast<int>(e);
+  pi_small_kernel<<<1, kSmallThreads, smem, static_cast<cudaStream_t>(stream)>>>(
+      view_of(g), v0, v_out, tie_mask, policy_kind, policy, gamma, threshold, max_steps, meta, last_delta_eval);
   GU_CHECK_LAUNCH();
   return GU_OK;
 }

@@ -3,19 +3,21 @@
 Same constructor, attributes, return conventions and error behaviour as
 core/envs/griduniverse_env.py:14-321 of the reference; the transition itself
 (`step` / `look_step_ahead`) runs in the batched CUDA kernel with a batch of one, so a
-single call costs one launch + one device->host read.  There is no CPU transition code in
+single call costs one launch + one stream synchronise (results land in pinned host memory).  There is no CPU transition code in
 this class: without a CUDA device `step` raises.  Use ``GridUniverseVecEnv`` for throughput.
 
 Not carried over: the pyglet viewer (`render(mode='graphic')`, `render_policy_arrows`) --
 GUI, out of scope.  `random_maze=True` works but uses this repo's own
 depth-first maze carver, so a given `random.seed` does not reproduce the reference's maze.
 """
+import ctypes
 import random
 import sys
 
 import numpy as np
 from six import StringIO
 
+from .. import _cabi
 from ..level import Level, parse_level_text, read_level_file
 from ..spaces import Discrete
 
@@ -35,6 +37,7 @@ class GridUniverseEnv(object):
             raise TypeError("grid_shape parameter must be tuple/list of two integers")
         self._device = device
         self._vec = None
+        self._scalar_io = None
         self.action_space = Discrete(4)
         self.action_descriptors = ['UP', 'RIGHT', 'DOWN', 'LEFT']
         self.action_descriptor_to_int = {desc: idx for idx, desc in enumerate(self.action_descriptors)}
@@ -104,9 +107,26 @@ class GridUniverseEnv(object):
             raise IndexError("list index out of range")
         if not 0 <= state < self.world.size:
             raise IndexError("index {} is out of bounds for axis 0 with size {}".format(state, self.world.size))
-        nxt, rew, term = self._device_env().look_step_ahead(np.array([state], np.int32),
-                                                            np.array([action], np.int32), care_about_terminal)
-        return int(nxt[0]), np.int64(rew[0]), bool(term[0])
+        # scalar fast path: the kernel reads (state, action) from and writes (next, reward, terminal)
+        # to one pinned host buffer directly (pinned memory is device-addressable under unified
+        # addressing), so a step is one launch and one stream synchronise -- no staging copies
+        vec = self._device_env()
+        io = self._scalar_io
+        if io is None:
+            import torch
+            io = self._scalar_io = torch.zeros(8, dtype=torch.int32).pin_memory()
+            self._scalar_np = io.numpy()
+            self._scalar_ptr = [ctypes.c_void_p(io.data_ptr() + 4 * k) for k in range(5)]
+        buf, ptr = self._scalar_np, self._scalar_ptr
+        buf[0], buf[1], buf[4] = state, action, 0
+        flags = 0 if care_about_terminal else _cabi.GU_FLAG_NO_CARE_TERMINAL
+        import torch
+        stream = torch.cuda.current_stream()
+        rc = vec._lib.gu_look_step_ahead(vec.levels.ref(), 1, ptr[0], ptr[1], ptr[2], ptr[3], ptr[4], flags,
+                                         ctypes.c_void_p(stream.cuda_stream))
+        _cabi.check("gu_look_step_ahead", rc)
+        stream.synchronize()
+        return int(buf[2]), np.int64(buf[3]), bool(buf[4] & 0xff)
 
     def look_step_ahead_batch(self, states, actions, care_about_terminal=True):
         """Vector form of look_step_ahead for many (state, action) pairs in one launch."""

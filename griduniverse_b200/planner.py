@@ -132,12 +132,26 @@ class Planner(object):
 
     # ------------------------------------------------------------------ policy iteration
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                         discount_factor=1.0):
+                         discount_factor=1.0, allow_small=True):
         """dynamic_programming.py:31-57.  Returns (V_lastconv_padded, tie_masks or None, sweeps,
         delta_eval, exhausted): tie masks are None when no greedy update ever ran (the caller's
         policy is returned unchanged in that case, as in the reference)."""
         kind, pol_t = self.stage_policy(policy)
         g = self.grid
+        if (allow_small and self._f64 and g.rows == g.Y and g.X * g.Y <= self._lib.gu_pi_small_max_cells()
+                and max_steps > 0):
+            v0 = self.stage_value(value_function)
+            v_out = g.empty()
+            tie = g.empty(torch.uint8)
+            meta = torch.zeros(3, dtype=torch.int32, device=self.device)
+            meta_d = torch.zeros(1, dtype=torch.float64, device=self.device)
+            rc = self._lib.gu_pi_small_f64(g.ref(), _cabi.ptr(v0), _cabi.ptr(v_out), _cabi.ptr(tie), kind,
+                                           _cabi.ptr(pol_t), float(discount_factor), float(threshold),
+                                           int(max_steps), _cabi.ptr(meta), _cabi.ptr(meta_d), _cabi.stream_ptr())
+            _cabi.check("gu_pi_small_f64", rc)
+            self.launches += 1
+            sweeps, improved, exhausted = (int(x) for x in meta.cpu().numpy())
+            return v_out, (tie if improved else None), sweeps, float(meta_d.item()), bool(exhausted)
         thr = self.np_dtype.type(threshold)
         v = self.stage_value(value_function)
         last = v

@@ -285,6 +285,17 @@ int gu_vi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* 
                     int32_t max_steps, int32_t* sweeps_out, double* last_delta, void* stream);
 int64_t gu_vi_small_max_cells(void);
 
+/* Whole policy_iteration loop (dynamic_programming.py:31-57) in one thread block, for whole
+ * grids of at most gu_pi_small_max_cells() cells: evaluate the current policy until
+ * max(V - V') < threshold, take the greedy policy of the result, stop when
+ * max(V_last_converged - V') < threshold or after max_steps sweeps.  Writes the last converged V,
+ * the tie masks of the final policy (only if an improvement ran: meta[1]) and
+ * meta = {sweeps, improved, exhausted}; exhausted = the reference's non-convergence warning. */
+int gu_pi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* tie_mask,
+                    int policy_kind, const void* policy, double gamma, double threshold,
+                    int32_t max_steps, int32_t* meta, double* last_delta_eval, void* stream);
+int64_t gu_pi_small_max_cells(void);
+
 /* ---- synthetic levels (not in the reference; pure functions of seed and index) -------- */
 
 /* Per-env levels for envs [first_env, first_env + n_envs): border open, 20 % interior walls,

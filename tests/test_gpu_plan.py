@@ -70,6 +70,25 @@ def test_dp_entry_points_bit_exact(golden, golden_levels, golden_cases, name):
     assert np.array_equal(policy_to_masks(P), golden["pi/%s/masks" % name])
 
 
+@pytest.mark.parametrize("name", DP_LEVELS)
+@pytest.mark.parametrize("gamma_theta_steps", [(0.9, 1e-6, 1000), (1.0, 0.001, 1000), (0.9, 1e-6, 7)])
+def test_policy_iteration_one_block_equals_multi_launch(golden_levels, name, gamma_theta_steps):
+    """The single-block policy-iteration kernel and the sweep-by-sweep driver agree bit for bit (V,
+    masks, sweep count, delta, warning flag), including the non-converging and max_steps cases."""
+    gamma, theta, steps = gamma_theta_steps
+    env = env_of(golden_levels, name)
+    N = env.world.size
+    pl = utils.planner_for(env)
+    rs = np.random.RandomState(1)
+    for policy in ("uniform", rs.dirichlet(np.ones(4), size=N)):
+        a = pl.policy_iteration(policy, np.zeros(N), theta, steps, gamma, allow_small=True)
+        b = pl.policy_iteration(policy, np.zeros(N), theta, steps, gamma, allow_small=False)
+        assert a[2:] == b[2:]
+        assert torch.equal(pl.grid.dense(a[0]), pl.grid.dense(b[0]))
+        assert (a[1] is None) == (b[1] is None)
+        assert a[1] is None or torch.equal(pl.grid.dense(a[1]), pl.grid.dense(b[1]))
+
+
 @pytest.mark.parametrize("name", ["default_env", "gen11_example", "test_env"])
 def test_gamma_one_defaults_and_warning(golden, golden_levels, golden_cases, name):
     """Default discount 1.0 with the example's settings: enclosed cells never converge, the
