@@ -8,9 +8,10 @@
  *
  * Conventions
  *  - extern "C", plain pointers and sizes.  Every pointer inside the descriptor
- *    structs and every array argument is a DEVICE pointer owned by the caller;
- *    the library never allocates, frees or keeps a pointer after the call.
- *    (`*_host` helpers are the exception and say so.)
+ *    structs and every array argument is a DEVICE-ACCESSIBLE pointer owned by the
+ *    caller (device memory; pinned host memory also works under unified addressing
+ *    and is what the single-env step path passes); the library never allocates,
+ *    frees or keeps a pointer after the call.
  *  - Every call only enqueues work on `stream` (a cudaStream_t passed as void*).
  *  - Return value: 0 = ok, <0 = argument error (GU_ERR_*), >0 = cudaError_t.
  *  - Grid geometry (core/envs/griduniverse_env.py:44-56): X = x_max columns,
