@@ -317,7 +317,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const bool has_l = active && lane == 0 && x0 > 0;   // edge lanes fetch one halo column each
   const bool has_r = active && lane == 31 && x0 + CPT < g.X;
   const bool full = x0 + CPT <= g.X;
-  const size_t pitch = g.pitch;
+  const int pitch = g.pitch;                         // element offsets fit in 31 bits (tiled_ok)
   const int hoff = has_l ? -1 : CPT;                  // halo column relative to x0
 
   WinRow<T, CPT, TIES> w[3];
@@ -331,14 +331,14 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const char* pf_base = nullptr;
   if (lane < kVLines) pf_base = reinterpret_cast<const char*>(vin + wx0) + lane * 128;
   else if (lane < kVLines + kILines) pf_base = reinterpret_cast<const char*>(info + wx0) + (lane - kVLines) * 128;
-  const size_t pf_pitch = lane < kVLines ? pitch * sizeof(T) : pitch;
+  const int pf_pitch = lane < kVLines ? pitch * static_cast<int>(sizeof(T)) : pitch;   // bytes; prefetch only
   const bool pf_on = pf_base != nullptr && wx0 + (lane < kVLines ? lane * (128 / static_cast<int>(sizeof(T))) : (lane - kVLines) * 128) < g.pitch;
 
   auto issue_loads = [&](int ar, WinRow<T, CPT, TIES>& r) {
-    const size_t o = static_cast<size_t>(ar) * pitch + x0;
+    const int o = ar * pitch + x0;
     if (pf_on) {
       const int par = min(ar + kPrefetchRows, rows + 1);
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + static_cast<size_t>(par) * pf_pitch));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_base + static_cast<size_t>(static_cast<unsigned>(par) * static_cast<unsigned>(pf_pitch))));
     }
     r.hv = T(0);
     r.hinfo = 0;
@@ -435,7 +435,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
           __syncwarp();                                  // this row's units from all lanes have landed
         }
         if (active) {
-          const size_t o = static_cast<size_t>(ry + 1) * pitch + x0;
+          const int o = (ry + 1) * pitch + x0;
           T out[CPT];
           uint32_t ties[IW];
           uint32_t pm[IW];
@@ -595,6 +595,10 @@ static inline GridView tview(const gu_grid* g) {
 static inline bool tiled_ok(const gu_grid* g, size_t elem, const void* a, const void* b) {
   if (g->info == nullptr) return false;
   if ((static_cast<size_t>(g->pitch) * elem) % 16 != 0 || g->pitch % 32 != 0) return false;
+  // the kernels index with 32-bit element offsets (and a 32-bit byte offset for the V prefetch)
+  if (static_cast<int64_t>(g->row_end - g->row_begin + 2) * g->pitch * static_cast<int64_t>(elem) >= (1ll << 32) ||
+      static_cast<int64_t>(g->row_end - g->row_begin + 2) * g->pitch >= (1ll << 31))
+    return false;
   if ((reinterpret_cast<uintptr_t>(a) & 15u) || (reinterpret_cast<uintptr_t>(b) & 15u)) return false;
   if (reinterpret_cast<uintptr_t>(g->info) & 3u) return false;
   return true;
