@@ -1,5 +1,6 @@
-"""The reference's example flows (examples/griduniverse_env_examples.py and
-examples/griduniverse_alg_examples.py) on the B200 path, plus the batched front end.
+"""The reference's example flows (examples/griduniverse_env_examples.py,
+examples/griduniverse_alg_examples.py and the core/algorithms/maze_solving.py script) on the B200
+path, plus the batched front end.
 
     python examples/griduniverse_examples.py            (needs a CUDA device)
 """
@@ -14,6 +15,7 @@ from griduniverse_b200.envs import GridUniverseEnv, GridUniverseVecEnv        # 
 from griduniverse_b200.algorithms import utils                                 # noqa: E402
 from griduniverse_b200.algorithms.monte_carlo import monte_carlo_evaluation, run_episode   # noqa: E402
 import griduniverse_b200.algorithms.dynamic_programming as dp                  # noqa: E402
+from griduniverse_b200.algorithms import maze_solving                          # noqa: E402
 
 
 def random_agent(env, max_steps=100, render=True):
@@ -79,8 +81,26 @@ def batched_demo(num_envs=65536, steps=256):
     return out
 
 
+def maze_solving_demo(world_shape=(15, 15)):
+    """Breadth-first path from the start to the nearest terminal, then walk it -- the flow of the
+    reference's maze_solving.py script on one random maze."""
+    env = GridUniverseEnv(grid_shape=world_shape, random_maze=True)
+    start = env.reset()
+    path = maze_solving.breadth_first_search(env, start)
+    print("maze solving: start %d, %d actions to a terminal: %s" % (start, len(path), path))
+    done = False
+    for action in path:
+        _, _, done, _ = env.step(action)
+    env.render()
+    assert done, "the breadth-first path must end on a terminal state"
+    dist = maze_solving.shortest_distances(env)
+    print("maze solving: %d of %d cells can reach the goal, farthest is %d actions away"
+          % (int((dist >= 0).sum()), env.world.size, int(dist.max())))
+
+
 if __name__ == '__main__':
     random_agent(GridUniverseEnv(), max_steps=20)
+    maze_solving_demo()
     planning_demo()
     monte_carlo_demo()
     batched_demo()
