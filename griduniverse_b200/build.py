@@ -41,9 +41,10 @@ def _sources():
 
 
 def _digest():
+    """Content hash of the sources (paths relative to the repo root, so any checkout agrees)."""
     h = hashlib.sha256()
     for p in _sources() + sorted(glob.glob(os.path.join(CSRC, "*.cuh"))) + sorted(glob.glob(os.path.join(INCLUDE, "*.h"))):
-        h.update(p.encode())
+        h.update(os.path.relpath(p, ROOT).encode())
         with open(p, "rb") as f:
             h.update(f.read())
     h.update(" ".join(NVCC_FLAGS).encode())
@@ -66,14 +67,30 @@ def build_library(force=False, verbose=False):
         with open(STAMP) as f:
             if f.read().strip() == digest:
                 return LIB_PATH
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-I", INCLUDE, "-I", CSRC, "-o", LIB_PATH] + _sources()
-    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
-    log = proc.stdout
+    # one nvcc -c per translation unit, in parallel (no cross-file device calls), then one link
+    obj_dir = os.path.join(LIB_DIR, "obj")
+    os.makedirs(obj_dir, exist_ok=True)
+    cflags = [f for f in NVCC_FLAGS if f != "--shared"]
+    jobs = []
+    for src in _sources():
+        obj = os.path.join(obj_dir, os.path.basename(src)[:-3] + ".o")
+        cmd = [_nvcc()] + cflags + ["-I", INCLUDE, "-I", CSRC, "-c", "-o", obj, src]
+        jobs.append((cmd, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    log, failed = "", False
+    for cmd, obj, proc in jobs:
+        out = proc.communicate()[0]
+        log += " ".join(cmd) + "\n" + out
+        failed = failed or proc.returncode != 0
+    if not failed:
+        cmd = [_nvcc(), "--shared", "-o", LIB_PATH] + [obj for _, obj, _ in jobs]
+        proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+        log += " ".join(cmd) + "\n" + proc.stdout
+        failed = proc.returncode != 0
     with open(os.path.join(LIB_DIR, "build.log"), "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if proc.returncode != 0:
+        f.write(log)
+    if failed:
         sys.stderr.write(log)
-        raise RuntimeError("nvcc failed building libgu_b200.so (exit %d)" % proc.returncode)
+        raise RuntimeError("nvcc failed building libgu_b200.so")
     if verbose:
         print(log)
     with open(STAMP, "w") as f:
