@@ -331,6 +331,60 @@ def run_ours(args):
     vi_e2e_value = io["sweeps"] * cells / t_vi_e2e
     clocks = sampler.stop() if sampler else None
 
+    # ------------------------------------------------------------------ cfg-5 parity record
+    # north_star cfg 5 (i): the sharded result is bit-identical to the single-GPU result.  Every rank
+    # also solves the WHOLE grid on its own GPU and compares its rows of V and of the tie masks byte
+    # for byte with what each multi-GPU driver produced; the digest is a checksum of per-2048-row
+    # checksums, so it is the same number at every N.
+    import hashlib
+
+    def block_digests(t, first_row):
+        out = []
+        assert first_row % 2048 == 0 and t.shape[0] % 2048 == 0, "digest blocks are 2048 rows: use N in 1, 2, 4, 8"
+        for b0 in range(0, t.shape[0], 2048):
+            out.append(hashlib.sha256(t[b0:b0 + 2048].contiguous().cpu().numpy().tobytes()).digest())
+        return out
+
+    def combined(digests_local):
+        """sha256 over the per-block digests of all ranks in row order (gathered on every rank)."""
+        mine = torch.tensor(list(b"".join(digests_local)), dtype=torch.uint8, device=dev)
+        if world > 1:
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            mine = torch.cat(parts)
+        return hashlib.sha256(bytes(mine.cpu().numpy().tobytes())).hexdigest()
+
+    v_s, tie_s, sw_s, _ = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
+    own_v, own_t = v_s[1:-1, :VI_SIZE], tie_s[1:-1, :VI_SIZE]
+    parity = {"ranks": world, "sweeps": sw_s, "sha256_V": combined(block_digests(own_v, r0)),
+              "sha256_ties": combined(block_digests(own_t, r0)),
+              "how": "sha256 over the sha256 of every 2048-row block of V (f32 bytes) / of the tie masks"}
+    if world > 1:
+        drivers = {("peer" if isinstance(svi, PeerValueIteration) else "nccl"): (own_v, own_t, sw_s)}
+        if isinstance(svi, PeerValueIteration):                     # the NCCL-driven arm as well
+            svi2 = ShardedValueIteration(pl)
+            v2, t2, sw2, _ = svi2.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
+            drivers["nccl"] = (v2[1:-1, :VI_SIZE], t2[1:-1, :VI_SIZE], sw2)
+        full = synth.maze_plan_grid(VI_SIZE, VI_SIZE, seed=0, dtype=np.float32, device=dev)
+        solo = ShardedValueIteration(Planner(None, np.float32, dev, grid=full), solo=True)
+        v1, t1, sw1, _ = solo.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
+        verdicts = {}
+        for name, (dv, dtie, dsw) in sorted(drivers.items()):
+            same = (dsw == sw1 and torch.equal(dv, v1[1 + r0:1 + r1, :VI_SIZE])
+                    and torch.equal(dtie, t1[1 + r0:1 + r1, :VI_SIZE]))
+            flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            verdicts[name] = bool(flag.item())
+        parity["drivers"] = verdicts
+        parity["bit_identical"] = all(verdicts.values())
+        parity["against"] = "a solo solve of the whole 16384x16384 grid on every rank's own GPU"
+        if rank == 0:      # the single-GPU digest, computed from rank 0's solo solve: must equal sha256_V
+            parity["sha256_V_single_gpu"] = hashlib.sha256(b"".join(block_digests(v1[1:-1, :VI_SIZE], 0))).hexdigest()
+        del full, solo, v1, t1
+    else:
+        parity["bit_identical"] = None     # N = 1 is the reference point: compare sha256_V across runs
+    torch.cuda.empty_cache()
+
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu_env = cpu_vi = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -374,6 +428,7 @@ def run_ours(args):
                 "e2e": {"value": vi_e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": io["h2d"] * world,
                         "d2h_bytes_per_step": io["d2h"] * world},
                 "gpu_launches": vi_launches, "collectives": vi_colls, "cpu_baseline": cpu_vi,
+                "parity": parity,
             },
             "cfg3": cfg3,
         }

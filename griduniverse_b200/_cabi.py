@@ -20,7 +20,7 @@ GU_TEXT_NO_START, GU_TEXT_NO_GOAL = -1, -2
 GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
 
 EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
-           "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_vi_small_f64",
+           "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_max_diff_f32", "gu_max_diff_f64", "gu_vi_small_f64",
            "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_version", "gu_arch", "gu_error_string")
 
 
@@ -46,7 +46,10 @@ class GuPeerLinks(ctypes.Structure):
     _fields_ = [("rank", ctypes.c_int32), ("world", ctypes.c_int32), ("slot", ctypes.c_int32),
                 ("n_slots", ctypes.c_int32), ("up_ghost", c_ptr), ("down_ghost", c_ptr),
                 ("res_tables", c_ptr * GU_MAX_PEERS), ("done_counter", c_ptr), ("error_flag", c_ptr),
-                ("threshold", ctypes.c_double)]
+                ("threshold", ctypes.c_double), ("gate_lag", ctypes.c_int32), ("first_slot", ctypes.c_int32),
+                ("halo_flags", c_ptr), ("up_flag", c_ptr), ("down_flag", c_ptr), ("edge_counters", c_ptr),
+                ("stop_flag", c_ptr), ("abort_flags", c_ptr * GU_MAX_PEERS), ("timeout_cycles", ctypes.c_int64),
+                ("slot_base", c_ptr)]
 
 
 class GuError(RuntimeError):
@@ -94,6 +97,8 @@ def lib():
         "gu_sweep_peer_f32": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f32, p, ctypes.POINTER(GuPeerLinks), p]),
         "gu_sweep_peer_f64": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f64, p, ctypes.POINTER(GuPeerLinks), p]),
         "gu_peer_wait": (ctypes.c_int, [ctypes.POINTER(GuPeerLinks), ctypes.c_int, p]),
+        "gu_max_diff_f32": (ctypes.c_int, [gp, p, p, p, p]),
+        "gu_max_diff_f64": (ctypes.c_int, [gp, p, p, p, p]),
         "gu_greedy_f64": (ctypes.c_int, [gp, p, p, f64, p]),
         "gu_greedy_f32": (ctypes.c_int, [gp, p, p, f32, p]),
         "gu_vi_small_f64": (ctypes.c_int, [gp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),

@@ -216,54 +216,100 @@ __device__ __forceinline__ float round_worst_init(float) { return CUDART_INF_F; 
 __device__ __forceinline__ double round_worst_init(double) { return 0.0; }
 
 // ---- NVLink peer-memory links of a row shard (fused halo exchange + residual all-reduce) --------
-// With PEER the sweep kernel replaces both collectives of the row-sharded value iteration:
+// With PEER the sweep kernel replaces both collectives of the row-sharded value iteration
+// (protocol: include/gu_b200.h, gu_peer_links):
 //  * the blocks that own the shard's first / last row also store their output vectors straight
-//    into the ghost row of the neighbour's v_out (peer memory over NVLink);
-//  * the last block to finish publishes the shard's residual into slot `slot` of every rank's
-//    residual table (release, system scope); the next sweep starts by waiting until all `world`
-//    entries of the previous slot have arrived in its local table -- their max is the gate.
-// A sweep gated off after convergence still publishes (the gate value), so waits always complete.
+//    into the ghost row of the neighbour's v_out (peer memory over NVLink); the last of them to
+//    finish raises the neighbour's halo flag to slot + 1.  Only the edge blocks of the next sweep
+//    wait, and only for their own neighbour's flag; they are scheduled first.
+//  * the last block of the shard publishes the shard's residual into slot `slot` of every rank's
+//    residual table; sweep `slot` gates on the complete row slot - lag (lag 2: the row has normally
+//    arrived long ago, so no rank stalls on the slowest one) and on the sticky stop word.
+//  * a wait that times out raises the abort word of every rank; aborted ranks stop writing.
 template <typename T>
 struct PeerArgs {
-  int rank, world, slot;
+  int rank, world, slot, lag, first_slot;
   T* up_ghost;                 // neighbour above: bottom ghost row of its v_out, or nullptr
   T* down_ghost;               // neighbour below: top ghost row of its v_out, or nullptr
   T* tables[GU_MAX_PEERS];     // rank r's residual table T[slots][world]; tables[rank] is local
+  int* aborts[GU_MAX_PEERS];   // rank r's abort word; aborts[rank] is local
   int* done;                   // local block counter, zero between launches
-  int* err;                    // local error flag (wait timed out)
+  int* err;                    // local error flag (a wait of this rank timed out)
+  int* halo;                   // local [2]: sweeps delivered from above / below
+  int* up_flag;                // neighbour above: its halo[1]
+  int* down_flag;              // neighbour below: its halo[0]
+  int* edge;                   // local [2]: finished blocks of the first / last block row
+  int* stop;                   // local sticky "converged" word
+  const int* slot_base;
+  long long timeout;
   T thr;
 };
 
 constexpr long long kPeerTimeoutCycles = 6000000000ll;   // ~3 s: give up instead of hanging the GPU
 
 template <typename T>
-__device__ __forceinline__ void peer_publish(const PeerArgs<T>& p, T val) {
-  __threadfence_system();
-  for (int r = 0; r < p.world; ++r)
-    *reinterpret_cast<volatile T*>(p.tables[r] + static_cast<size_t>(p.slot) * p.world + p.rank) = val;
+__device__ __noinline__ void peer_abort(const PeerArgs<T>& p) {
+  *reinterpret_cast<volatile int*>(p.err) = 1;
+  for (int r = 0; r < p.world; ++r) *reinterpret_cast<volatile int*>(p.aborts[r]) = 1;
   __threadfence_system();
 }
 
-// max over all ranks of slot `slot` of the local table, spinning until every entry has arrived
 template <typename T>
-__device__ __forceinline__ T peer_wait_slot(const PeerArgs<T>& p, int slot, bool acquire = true) {
+__device__ __forceinline__ bool peer_aborted(const PeerArgs<T>& p) {
+  return *reinterpret_cast<const volatile int*>(p.aborts[p.rank]) != 0;
+}
+
+template <typename T>
+__device__ __forceinline__ void peer_publish(const PeerArgs<T>& p, int slot, T val) {
+  __threadfence_system();
+  for (int r = 0; r < p.world; ++r)
+    *reinterpret_cast<volatile T*>(p.tables[r] + static_cast<size_t>(slot) * p.world + p.rank) = val;
+  __threadfence_system();
+}
+
+// max over all ranks of slot `slot` of the local table, spinning until every entry has arrived.
+// false = aborted (this rank's wait timed out, or another rank raised the abort word).
+template <typename T>
+__device__ __forceinline__ bool peer_wait_slot(const PeerArgs<T>& p, int slot, T& out) {
   const volatile T* tab = p.tables[p.rank] + static_cast<size_t>(slot) * p.world;
   T m = Num<T>::neg_inf();
-  const long long t0 = clock64();
+  long long t0 = 0;
   for (int r = 0; r < p.world; ++r) {
     T v = tab[r];
     while (v != v) {                              // NaN = not written yet
-      if (clock64() - t0 > kPeerTimeoutCycles) { *p.err = 1; v = -Num<T>::neg_inf(); break; }
+      if (t0 == 0) t0 = clock64();
+      if (peer_aborted(p)) return false;
+      if (clock64() - t0 > p.timeout) { peer_abort(p); return false; }
       v = tab[r];
     }
     m = v > m ? v : m;
   }
-  if (acquire) __threadfence_system();   // only readers of peer-written ghost rows need the system fence
-  return m;
+  out = m;
+  return true;
+}
+
+// spin until *word >= target (a neighbour's halo flag)
+template <typename T>
+__device__ __forceinline__ bool peer_wait_flag(const PeerArgs<T>& p, const int* word, int target) {
+  const volatile int* w = word;
+  if (*w >= target) return true;
+  const long long t0 = clock64();
+  while (*w < target) {
+    if (peer_aborted(p)) return false;
+    if (clock64() - t0 > p.timeout) { peer_abort(p); return false; }
+  }
+  return true;
 }
 
 template <typename T>
-__global__ void peer_wait_kernel(PeerArgs<T> p) { (void)peer_wait_slot(p, p.slot); }
+__global__ void peer_wait_kernel(PeerArgs<T> p) {
+  const int slot = p.slot + (p.slot_base ? *p.slot_base : 0);
+  T m;
+  if (!peer_wait_slot(p, slot, m)) return;
+  if (p.up_flag && !peer_wait_flag(p, p.halo + 0, slot + 1)) return;
+  if (p.down_flag && !peer_wait_flag(p, p.halo + 1, slot + 1)) return;
+  __threadfence_system();
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -291,19 +337,40 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   constexpr int UPT = CPT * static_cast<int>(sizeof(T)) / 4;
   constexpr int kStage = 32 * UPT + 32;
   __shared__ __align__(16) uint4 pstage[KIND == GU_POLICY_PROBS ? kTiledWarps * 2 * kStage : 1];
+  int by = blockIdx.y;
+  int slot = 0;
+  bool top_edge = false, bot_edge = false;
   if (!PEER) {
     if (gate != nullptr && *gate < gate_thr) return;
-  } else if (peer.slot > 0) {
-    __shared__ T gate_sh;
-    // blocks that read a ghost row (first / last block row) acquire at system scope; the others only
-    // need the gate value itself
-    const bool edge_block = blockIdx.y == 0 || blockIdx.y == gridDim.y - 1;
-    if (threadIdx.x == 0) gate_sh = peer_wait_slot(peer, peer.slot - 1, edge_block);
-    __syncthreads();
-    if (gate_sh < peer.thr) {                 // converged earlier: pass the verdict on, keep V
-      if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) peer_publish(peer, gate_sh);
-      return;
+  } else {
+    // the two edge block rows are scheduled first: their rows travel while the interior computes
+    const int nby = gridDim.y;
+    if (nby >= 3) by = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? nby - 1 : static_cast<int>(blockIdx.y) - 1);
+    top_edge = by == 0 && peer.up_flag != nullptr;
+    bot_edge = by == nby - 1 && peer.down_flag != nullptr;
+    slot = peer.slot + (peer.slot_base != nullptr ? *peer.slot_base : 0);
+    __shared__ int go_sh;
+    if (threadIdx.x == 0) {
+      int go = 1;
+      if (peer_aborted(peer) || *reinterpret_cast<const volatile int*>(peer.stop) != 0) {
+        go = 0;
+      } else {
+        const int gslot = slot - peer.lag;
+        if (gslot >= peer.first_slot) {
+          T m;
+          if (!peer_wait_slot(peer, gslot, m)) go = 0;
+          else if (m < peer.thr) { *reinterpret_cast<volatile int*>(peer.stop) = 1; go = 0; }   // converged earlier: keep V
+        }
+        if (go && slot > peer.first_slot) {
+          if (top_edge && !peer_wait_flag(peer, peer.halo + 0, slot)) go = 0;
+          if (go && bot_edge && !peer_wait_flag(peer, peer.halo + 1, slot)) go = 0;
+          if (top_edge || bot_edge) __threadfence_system();     // acquire the neighbour's rows
+        }
+      }
+      go_sh = go;
     }
+    __syncthreads();
+    if (!go_sh) return;
   }
   init_luts(luts);
   __syncthreads();
@@ -311,7 +378,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const int lane = threadIdx.x & 31;
   const int x0 = ((blockIdx.x * kTiledWarps + (threadIdx.x >> 5)) * 32 + lane) * CPT;
   const int rows = g.row_end - g.row_begin;
-  const int ry0 = blockIdx.y * rows_per_block;
+  const int ry0 = by * rows_per_block;
   const int ry1 = min(ry0 + rows_per_block, rows);
   const bool active = x0 < g.X;                       // lanes past the grid still take part in shuffles
   const bool has_l = active && lane == 0 && x0 > 0;   // edge lanes fetch one halo column each
@@ -538,21 +605,36 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     dmax = warp_max(dmax);
     if (lane == 0) scratch[threadIdx.x >> 5] = dmax;
     // ghost-row stores of the first / last block row are out (system scope) before the block reports
-    if (PEER && (blockIdx.y == 0 || blockIdx.y == gridDim.y - 1)) __threadfence_system();
+    if (PEER && (top_edge || bot_edge)) __threadfence_system();
     __syncthreads();
-    if (threadIdx.x == 0 && residual != nullptr) {
-      T m = scratch[0];
-#pragma unroll
-      for (int k = 1; k < kTiledWarps; ++k) m = scratch[k] > m ? scratch[k] : m;
-      atomic_max_signed(residual, m);
+    if (threadIdx.x == 0) {
       if (PEER) {
-        __threadfence();
-        const int nblocks = gridDim.x * gridDim.y;
-        if (atomicAdd(peer.done, 1) == nblocks - 1) {     // last block of the sweep
+        // the last block of an edge block row raises the neighbour's halo flag
+        if (top_edge && atomicAdd(peer.edge + 0, 1) == static_cast<int>(gridDim.x) - 1) {
+          peer.edge[0] = 0;
+          __threadfence_system();
+          *reinterpret_cast<volatile int*>(peer.up_flag) = slot + 1;
+        }
+        if (bot_edge && atomicAdd(peer.edge + 1, 1) == static_cast<int>(gridDim.x) - 1) {
+          peer.edge[1] = 0;
+          __threadfence_system();
+          *reinterpret_cast<volatile int*>(peer.down_flag) = slot + 1;
+        }
+      }
+      if (residual != nullptr) {
+        T m = scratch[0];
+#pragma unroll
+        for (int k = 1; k < kTiledWarps; ++k) m = scratch[k] > m ? scratch[k] : m;
+        atomic_max_signed(residual, m);
+        if (PEER) {
           __threadfence();
-          const T fin = *reinterpret_cast<volatile T*>(residual);
-          *peer.done = 0;
-          peer_publish(peer, fin);
+          const int nblocks = gridDim.x * gridDim.y;
+          if (atomicAdd(peer.done, 1) == nblocks - 1) {     // last block of the sweep
+            __threadfence();
+            const T fin = *reinterpret_cast<volatile T*>(residual);
+            *peer.done = 0;
+            peer_publish(peer, slot, fin);
+          }
         }
       }
     }
@@ -650,17 +732,28 @@ static int choose_rows_per_block(K kernel, int rows, int blocks_x) {
 
 template <typename T>
 static int make_peer_args(const gu_peer_links* pl, PeerArgs<T>* out) {
-  if (!pl || !pl->done_counter || !pl->error_flag) return GU_ERR_NULL;
+  if (!pl || !pl->done_counter || !pl->error_flag || !pl->halo_flags || !pl->edge_counters || !pl->stop_flag)
+    return GU_ERR_NULL;
   if (pl->world < 1 || pl->world > GU_MAX_PEERS || pl->rank < 0 || pl->rank >= pl->world || pl->slot < 0 ||
-      pl->slot >= pl->n_slots)
+      pl->slot >= pl->n_slots || pl->gate_lag < 1 || pl->gate_lag > 2 || pl->first_slot < 0)
     return GU_ERR_SHAPE;
   out->rank = pl->rank; out->world = pl->world; out->slot = pl->slot;
+  out->lag = pl->gate_lag; out->first_slot = pl->first_slot;
   out->up_ghost = static_cast<T*>(pl->up_ghost);
   out->down_ghost = static_cast<T*>(pl->down_ghost);
-  for (int r = 0; r < GU_MAX_PEERS; ++r) out->tables[r] = r < pl->world ? static_cast<T*>(pl->res_tables[r]) : nullptr;
+  for (int r = 0; r < GU_MAX_PEERS; ++r) {
+    out->tables[r] = r < pl->world ? static_cast<T*>(pl->res_tables[r]) : nullptr;
+    out->aborts[r] = r < pl->world ? pl->abort_flags[r] : nullptr;
+  }
   for (int r = 0; r < pl->world; ++r)
-    if (!out->tables[r]) return GU_ERR_NULL;
+    if (!out->tables[r] || !out->aborts[r]) return GU_ERR_NULL;
+  // a neighbour is described by its ghost row AND its flag word, or by neither
+  if ((pl->up_ghost == nullptr) != (pl->up_flag == nullptr) || (pl->down_ghost == nullptr) != (pl->down_flag == nullptr))
+    return GU_ERR_NULL;
   out->done = pl->done_counter; out->err = pl->error_flag;
+  out->halo = pl->halo_flags; out->up_flag = pl->up_flag; out->down_flag = pl->down_flag;
+  out->edge = pl->edge_counters; out->stop = pl->stop_flag; out->slot_base = pl->slot_base;
+  out->timeout = pl->timeout_cycles > 0 ? pl->timeout_cycles : kPeerTimeoutCycles;
   out->thr = static_cast<T>(pl->threshold);
   return GU_OK;
 }
@@ -789,6 +882,45 @@ extern "C" __attribute__((visibility("default"))) int gu_peer_wait(const gu_peer
   }
   GU_CHECK_LAUNCH();
   return GU_OK;
+}
+
+// signed max of (a - b) over the owned cells of a shard (dynamic_programming.py:44)
+namespace gu {
+template <typename T>
+__global__ void __launch_bounds__(256)
+max_diff_kernel(int X, int rows, int pitch, const T* __restrict__ a, const T* __restrict__ b, T* out) {
+  __shared__ T scratch[8];
+  T m = Num<T>::neg_inf();
+  const int x4 = (blockIdx.x * 256 + threadIdx.x) * 4;
+  if (x4 < X) {
+    for (int ry = blockIdx.y; ry < rows; ry += gridDim.y) {
+      const size_t o = static_cast<size_t>(ry + 1) * pitch + x4;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (x4 + j < X) m = max_nn(m, Num<T>::add(a[o + j], -b[o + j]));
+    }
+  }
+  block_max_to_global(m, scratch, out);
+}
+template <typename T>
+static int launch_max_diff(const gu_grid* g, const T* a, const T* b, T* out, cudaStream_t st) {
+  if (!g || !a || !b || !out) return GU_ERR_NULL;
+  if (g->X <= 0 || g->row_end <= g->row_begin || g->pitch < g->X) return GU_ERR_SHAPE;
+  const int rows = g->row_end - g->row_begin;
+  dim3 grid((g->X + 1023) / 1024, rows < 592 ? rows : 592);
+  max_diff_kernel<T><<<grid, 256, 0, st>>>(g->X, rows, g->pitch, a, b, out);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+}  // namespace gu
+
+extern "C" __attribute__((visibility("default"))) int gu_max_diff_f32(const gu_grid* g, const float* a, const float* b,
+                                                                        float* out, void* stream) {
+  return gu::launch_max_diff<float>(g, a, b, out, static_cast<cudaStream_t>(stream));
+}
+extern "C" __attribute__((visibility("default"))) int gu_max_diff_f64(const gu_grid* g, const double* a,
+                                                                        const double* b, double* out, void* stream) {
+  return gu::launch_max_diff<double>(g, a, b, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int gu_pack_info(const gu_grid* g, uint8_t* info, void* stream) {

@@ -89,6 +89,14 @@ class Planner(object):
         self.launches += 1
         return out
 
+    def max_diff(self, a, b):
+        """Signed max of (a - b) over the owned cells as a device scalar (dynamic_programming.py:44)."""
+        out = self.new_residuals(1)
+        fn = self._lib.gu_max_diff_f64 if self._f64 else self._lib.gu_max_diff_f32
+        _cabi.check("gu_max_diff", fn(self.grid.ref(), _cabi.ptr(a), _cabi.ptr(b), _cabi.ptr(out), _cabi.stream_ptr()))
+        self.launches += 1
+        return out
+
     def new_residuals(self, n):
         return torch.full((n,), float("-inf"), dtype=self.dtype, device=self.device)
 
@@ -127,12 +135,13 @@ class Planner(object):
         from .sharded import ShardedValueIteration      # one driver for one GPU and for row shards
         if getattr(self, "_solo_driver", None) is None:
             self._solo_driver = ShardedValueIteration(self, solo=True)
-        return self._solo_driver.value_iteration((kind0, pol_t), v0, threshold, max_steps, discount_factor,
-                                                 chunk=chunk, use_graph=use_graph)
+        v, tie, sweeps, last = self._solo_driver.value_iteration((kind0, pol_t), v0, threshold, max_steps,
+                                                                 discount_factor, chunk=chunk, use_graph=use_graph)
+        return v.clone(), tie, sweeps, last      # v is a view of the driver's persistent buffers
 
     # ------------------------------------------------------------------ policy iteration
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                         discount_factor=1.0, allow_small=True):
+                         discount_factor=1.0, allow_small=True, chunk=16, use_graph=True):
         """dynamic_programming.py:31-57.  Returns (V_lastconv_padded, tie_masks or None, sweeps,
         delta_eval, exhausted): tie masks are None when no greedy update ever ran (the caller's
         policy is returned unchanged in that case, as in the reference)."""
@@ -152,29 +161,10 @@ class Planner(object):
             self.launches += 1
             sweeps, improved, exhausted = (int(x) for x in meta.cpu().numpy())
             return v_out, (tie if improved else None), sweeps, float(meta_d.item()), bool(exhausted)
-        thr = self.np_dtype.type(threshold)
-        v = self.stage_value(value_function)
-        last = v
-        pool = [v, g.empty(), g.empty()]     # current, last converged, scratch
-        res = self.new_residuals(max(max_steps, 1))
-        tie = None
-        sweeps = 0
-        delta_eval = float("nan")
-        exhausted = False
-        for step in range(max_steps):
-            out = next(b for b in pool if b is not v and b is not last)
-            self.sweep(v, out, kind, pol_t, discount_factor, res[step:step + 1])
-            sweeps += 1
-            delta_eval = res[step].item()
-            v = out
-            if self.np_dtype.type(delta_eval) < thr:          # policy evaluation converged (:42)
-                tie = self.greedy(v, discount_factor, tie)     # in-place policy update (:43, utils.py:69)
-                delta = (g.dense(last) - g.dense(v)).max().item()
-                last = v
-                kind, pol_t = _cabi.GU_POLICY_MASK, tie
-                if self.np_dtype.type(delta) < thr:
-                    break
-            elif step == max_steps - 1:
-                tie = self.greedy(last, discount_factor, tie)
-                exhausted = True
-        return last, tie, sweeps, delta_eval, exhausted
+        if getattr(self, "_solo_driver", None) is None:
+            from .sharded import ShardedValueIteration
+            self._solo_driver = ShardedValueIteration(self, solo=True)
+        last, tie, sweeps, delta_eval, exhausted = self._solo_driver.policy_iteration(
+            (kind, pol_t), value_function, threshold, max_steps, discount_factor, chunk=chunk, use_graph=use_graph)
+        # the driver's buffers are reused by the next solve: hand out copies
+        return last.clone(), (None if tie is None else tie.clone()), sweeps, delta_eval, exhausted

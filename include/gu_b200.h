@@ -209,18 +209,36 @@ int gu_sweep_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_k
 
 /* Row-sharded sweeps fused with their collectives over NVLink peer memory (no NCCL in the
  * loop).  Each rank passes pointers into its neighbours' and peers' memory (e.g. from
- * torch.distributed._symmetric_memory):
- *   up_ghost / down_ghost: the ghost row of the neighbour's v_out that mirrors this shard's
- *     first / last row (NULL at the grid edge).  The kernel stores those rows there directly.
- *   res_tables[r]: rank r's residual table T[n_slots][world], NaN-initialised; res_tables[rank]
- *     is this rank's own.  Sweep number `slot` writes max(v_in - v_out) of the shard to entry
- *     [slot][rank] of EVERY table when its last block finishes; sweep slot+1 first waits until
- *     all `world` entries of [slot] have arrived locally and is a no-op (republishing the value)
- *     if their max is below `threshold` -- the reference's stopping rule
- *     (dynamic_programming.py:17,22-23) evaluated identically on every rank.
- *   residual: local T scalar for this sweep, initialised to -inf; done_counter: local int32 = 0.
- * Needs the tiled layout (info plane, pitch % 32 == 0).  gu_peer_wait blocks the stream until
- * slot `slot` is complete (use before the host reads the table). */
+ * torch.distributed._symmetric_memory).  Sweep number `slot` (0, 1, 2, ... within one solve):
+ *   halo exchange   the blocks that own the shard's first / last row also store their output rows
+ *     into `up_ghost` / `down_ghost`, the ghost row of the neighbour's v_out that mirrors them (NULL at
+ *     the grid edge).  When the last of those blocks is done it stores slot+1 into the neighbour's
+ *     flag word (`up_flag` / `down_flag`, pointing at the neighbour's halo_flags[1] / halo_flags[0]).
+ *     Only the first / last block row of sweep slot >= 1 waits, and only for its own neighbour:
+ *     halo_flags[0] >= slot (rows from above have arrived, and the neighbour above has finished
+ *     reading the ghost row this sweep is about to overwrite), halo_flags[1] >= slot likewise.
+ *     Those blocks are scheduled first, so the rows travel while the interior is computed.
+ *   residual / stopping rule   when the last block of the shard finishes, max(v_in - v_out) of the
+ *     shard goes to entry [slot][rank] of EVERY rank's residual table res_tables[r]
+ *     (T[n_slots][world], NaN = not written yet; res_tables[rank] is this rank's own).  Sweep `slot`
+ *     checks the slot `slot - gate_lag` (only slots >= first_slot): it waits until all `world` entries
+ *     have arrived locally and, if their max is below `threshold`, is a no-op and sets the sticky word
+ *     `stop_flag`, which turns every later sweep into a no-op too.  This is the reference's stopping
+ *     rule (dynamic_programming.py:17,22-23) evaluated identically on every rank.  gate_lag = 1 stops
+ *     exactly after the converged sweep; gate_lag = 2 (the default driver) lets one more sweep run
+ *     into the OTHER ping-pong buffer, so the converged V is intact and no rank ever stalls on the
+ *     slowest rank's residual.
+ *   errors   every wait gives up after `timeout_cycles` (0 = about 3 s): the rank sets `error_flag`,
+ *     stores 1 into every rank's abort word (`abort_flags[r]`, this rank's own included) and stops
+ *     writing; a rank that finds its abort word set skips all remaining work, so the host of EVERY
+ *     rank sees the failure at its next check instead of consuming stale ghost rows.
+ *   slot_base (optional, device int32): the effective slot is slot + *slot_base, so a captured CUDA
+ *     graph of a chunk of sweeps can be replayed with only that word changing.
+ *   residual: local T scalar of this sweep, initialised to -inf; done_counter int32 and
+ *     edge_counters int32[2]: local, zero between launches.
+ * Needs the tiled layout (info plane, pitch % 32 == 0).  gu_peer_wait blocks the stream until every
+ * entry of slot `slot` has arrived and both neighbours have delivered the rows of that sweep (use it
+ * before reading the table or the ghost rows on the host / in another kernel). */
 #define GU_MAX_PEERS 16
 typedef struct {
   int32_t rank, world;
@@ -231,6 +249,16 @@ typedef struct {
   int32_t* done_counter;
   int32_t* error_flag;
   double threshold;
+  int32_t gate_lag;             /* 1 or 2 */
+  int32_t first_slot;           /* slots below this one belong to an earlier phase and are never gated on */
+  int32_t* halo_flags;          /* local int32[2]: sweeps delivered by the neighbour above / below */
+  int32_t* up_flag;             /* neighbour above: its halo_flags + 1, or NULL */
+  int32_t* down_flag;           /* neighbour below: its halo_flags + 0, or NULL */
+  int32_t* edge_counters;       /* local int32[2] */
+  int32_t* stop_flag;           /* local int32, sticky "converged" */
+  int32_t* abort_flags[GU_MAX_PEERS];
+  int64_t timeout_cycles;
+  const int32_t* slot_base;
 } gu_peer_links;
 
 int gu_sweep_peer_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_kind,
@@ -240,6 +268,12 @@ int gu_sweep_peer_f64(const gu_grid* g, const double* v_in, double* v_out, int p
                       const void* policy, double gamma, double* residual, const gu_peer_links* peer,
                       void* stream);
 int gu_peer_wait(const gu_peer_links* peer, int is_f64, void* stream);
+
+/* Signed max of (a - b) over the shard's owned cells (x < X), combined into *out by atomic max
+ * (caller initialises *out to -inf): np.max(last_converged_v_fun - new_value_function),
+ * dynamic_programming.py:44.  a, b: padded per-cell arrays of the grid layout. */
+int gu_max_diff_f32(const gu_grid* g, const float* a, const float* b, float* out, void* stream);
+int gu_max_diff_f64(const gu_grid* g, const double* a, const double* b, double* out, void* stream);
 
 /* greedy_policy_from_value_function (utils.py:55-72) as a tie mask per cell:
  * bit a set <=> rint(q[s,a]*1e8) == rint(max_a q[s,a]*1e8) and s is not terminal,
