@@ -43,6 +43,9 @@ template <typename T>
 struct Luts {
   T reward[4][2];   // [goal | lava<<1] -> {R (griduniverse_env.py:80-90), poison: 0 or NaN for terminals}
   T inv_cnt[8];     // 1/len(ties) at index len: exact 1, 1/2, 1/3 (correctly rounded), 1/4
+  // [len(ties) << 2 | goal | lava<<1] -> {1/len(ties), or 0 in a terminal cell (utils.py:70); R[s]}:
+  // one index serves the probability and the reward, and terminals need no NaN "poison"
+  T prs[32][2];
 };
 
 template <typename T>
@@ -53,6 +56,10 @@ __device__ __forceinline__ void init_luts(Luts<T>& l) {
     l.reward[t][1] = t ? T(CUDART_NAN) : T(0);
   }
   if (t < 8) l.inv_cnt[t] = Num<T>::inv(t);
+  if (t < 32) {
+    l.prs[t][0] = (t & 3) ? T(0) : Num<T>::inv(t >> 2);
+    l.prs[t][1] = (t & 2) ? T(-10) : ((t & 1) ? T(10) : T(-1));
+  }
 }
 
 template <typename T>
@@ -130,6 +137,71 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
       : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
         "d"(ga[3]), "r"(lut));
   return acc;
+}
+
+// ---- f32x2 formulation (sm_100a FMUL2 / FADD2 / FFMA2) ------------------------------------------------
+// The fused-greedy sweep is bound by instruction issue and by the half-rate ALU pipe (selects,
+// compares, min/max), not by HBM.  Blackwell's packed f32x2 instructions do two IEEE fp32 operations
+// per issue slot (measured on B200, tools/ubench/pipes.cu: 2 cycles per warp instruction, and they
+// co-issue with ALU-pipe instructions), so every multiply / add of the backup is done for two
+// neighbouring cells at once -- same operations, same order, same roundings per lane as the scalar
+// form; the freed issue slots go to the ALU pipe.
+#ifndef GU_F32_PACK
+#define GU_F32_PACK 1
+#endif
+#ifndef GU_F32_PACK_FOLD
+#define GU_F32_PACK_FOLD 1      // acc = fma(w, p*g, acc): exact for w in {0, 1}, one packed op instead of two
+#endif
+#ifndef GU_F32_PACK_W
+#define GU_F32_PACK_W 0         // 1: tie weights on the FMA pipe (max(ra - m + 1, 0)) instead of FSET
+#endif
+
+__device__ __forceinline__ float lds_f32(const void* base, uint32_t off) {
+  return *reinterpret_cast<const float*>(static_cast<const char*>(base) + off);
+}
+
+// Backup of two neighbouring cells.  ra*/ga*: rounded scaled q-value / discounted value of the
+// landing cell per action; m*: max of ra*; off*: (goal | lava << 1) << 3 of the cell.
+// Terminal cells: all four actions are blocked, so all tie and the count is 4; the table entry then
+// holds p = 0 and the sum stays R[s] + (+-0) = R[s] (utils.py:70).
+__device__ __forceinline__ void backup_ties_pair(const float (&ra0)[4], const float (&ra1)[4], float m0, float m1,
+                                                 const float (&ga0)[4], const float (&ga1)[4], uint32_t off0,
+                                                 uint32_t off1, const Luts<float>& l, float& out0, float& out1) {
+  float2 w[4];
+#if GU_F32_PACK_W
+  // ra, m are integer-valued (rint), ra <= m: ra - m is exact 0 for a tie and <= -1 otherwise
+  const float2 nm = make_float2(-m0, -m1), one = make_float2(1.0f, 1.0f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float2 u = __fadd2_rn(__fadd2_rn(make_float2(ra0[a], ra1[a]), nm), one);
+    w[a] = make_float2(fmaxf(u.x, 0.0f), fmaxf(u.y, 0.0f));
+  }
+#else
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(w[a].x) : "f"(ra0[a]), "f"(m0));
+    asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(w[a].y) : "f"(ra1[a]), "f"(m1));
+  }
+#endif
+  // count of ties in mantissa bits 5-7 of a magic-number sum
+  float2 c = make_float2(8388608.0f, 8388608.0f);
+  const float2 k32 = make_float2(32.0f, 32.0f);
+#pragma unroll
+  for (int a = 0; a < 4; ++a) c = __ffma2_rn(w[a], k32, c);
+  const uint32_t i0 = (__float_as_uint(c.x) & 0xe0u) | off0, i1 = (__float_as_uint(c.y) & 0xe0u) | off1;
+  const float2 p = make_float2(lds_f32(&l.prs[0][0], i0), lds_f32(&l.prs[0][0], i1));
+  float2 acc = make_float2(lds_f32(&l.prs[0][1], i0), lds_f32(&l.prs[0][1], i1));      // R[s]
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    const float2 pg = __fmul2_rn(p, make_float2(ga0[a], ga1[a]));
+#if GU_F32_PACK_FOLD
+    acc = __ffma2_rn(w[a], pg, acc);
+#else
+    acc = __fadd2_rn(acc, __fmul2_rn(w[a], pg));
+#endif
+  }
+  out0 = acc.x;
+  out1 = acc.y;
 }
 
 #ifndef GU_TILED_WARPS
@@ -315,8 +387,11 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+#ifndef GU_TILED_MIN_BLOCKS
+#define GU_TILED_MIN_BLOCKS 3       // fp32: 3 blocks x 4 warps per SM, up to 168 registers per thread (no spills)
+#endif
 template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false>
-__global__ void __launch_bounds__(kTiledWarps * 32)
+__global__ void __launch_bounds__(kTiledWarps * 32, (sizeof(T) == 4 ? GU_TILED_MIN_BLOCKS : 1))
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
                    T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block,
@@ -327,6 +402,8 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   constexpr int CPT = W * NV;                 // cells per thread: NV 16-byte vectors
   constexpr int IW = CPT / 4 ? CPT / 4 : 1;   // 32-bit words of info per thread-row
   constexpr bool TIES = (KIND == GU_POLICY_GREEDY) || WRITE_TIE;
+  // f32x2 arithmetic for pairs of neighbouring cells (fp32 only; rint via FRND, no slow path)
+  constexpr bool kPack = GU_F32_PACK && GU_F32_FRND && sizeof(T) == 4 && CPT % 2 == 0;
   __shared__ T scratch[kTiledWarps];
   __shared__ __align__(16) Luts<T> luts;
   // GU_POLICY_PROBS: a thread's CPT cells own CPT*4 probabilities = UPT 16-byte units that sit 128
@@ -429,11 +506,39 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   auto convert = [&](WinRow<T, CPT, TIES>& r) {
     T worst = round_worst_init(T(0));
     T ht = T(0);
+    if constexpr (kPack) {
 #pragma unroll
-    for (int j = 0; j < CPT; ++j) {
-      r.g[j] = N::mul(gamma, r.v[j]);
-      if constexpr (TIES)
-        r.rt[j] = round_fast(N::mul(N::add(reward_at(luts, lut_offset<T>(r.info, j)), r.g[j]), N::scale()), worst);
+      for (int j = 0; j < CPT; j += 2) {
+        // ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 when the product has no other use, even
+        // with --fmad=false (and it rewrites fma(g, 1, R) to that add first).  In the sweep kernels g
+        // lives on in the window, so the packed pair stays unfused (checked in SASS: FMUL2 + FADD2); the
+        // greedy-extraction kernel has no other use for g and takes the scalar .rn forms, which are
+        // never contracted.
+        float2 g2, s2;
+        const float2 rw = make_float2(TIES ? reward_at(luts, lut_offset<T>(r.info, j)) : 0.0f,
+                                      TIES ? reward_at(luts, lut_offset<T>(r.info, j + 1)) : 0.0f);
+        if constexpr (WRITE_TIE) {
+          g2 = make_float2(__fmul_rn(gamma, r.v[j]), __fmul_rn(gamma, r.v[j + 1]));
+          s2 = make_float2(__fadd_rn(rw.x, g2.x), __fadd_rn(rw.y, g2.y));
+        } else {
+          g2 = __fmul2_rn(make_float2(gamma, gamma), make_float2(r.v[j], r.v[j + 1]));
+          if constexpr (TIES) s2 = __fadd2_rn(rw, g2);
+        }
+        r.g[j] = g2.x;
+        r.g[j + 1] = g2.y;
+        if constexpr (TIES) {
+          const float2 t2 = __fmul2_rn(s2, make_float2(1e8f, 1e8f));
+          r.rt[j] = rintf(t2.x);
+          r.rt[j + 1] = rintf(t2.y);
+        }
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < CPT; ++j) {
+        r.g[j] = N::mul(gamma, r.v[j]);
+        if constexpr (TIES)
+          r.rt[j] = round_fast(N::mul(N::add(reward_at(luts, lut_offset<T>(r.info, j)), r.g[j]), N::scale()), worst);
+      }
     }
     const T hg = N::mul(gamma, r.hv);
     if constexpr (TIES) {
@@ -516,57 +621,85 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               for (int k = 0; k < IW; ++k) pm[k] = *reinterpret_cast<const uint32_t*>(pp + 4 * k);
             }
           }
+          if constexpr (kPack && KIND == GU_POLICY_GREEDY && !WRITE_TIE) {
 #pragma unroll
-          for (int c = 0; c < CPT; ++c) {
-            const uint32_t inf = info_of(cur.info, c);
-            const T gs = cur.g[c];
-            // discounted value of the landing cell per action: UP, RIGHT, DOWN, LEFT
-            T ga[4];
-            ga[0] = (inf & kBlkU) ? gs : up.g[c];
-            ga[1] = (inf & kBlkR) ? gs : (c == CPT - 1 ? cur.gr : cur.g[c + 1 < CPT ? c + 1 : c]);
-            ga[2] = (inf & kBlkD) ? gs : dn.g[c];
-            ga[3] = (inf & kBlkL) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
-            const auto rp = reward_poison_at(luts, lut_offset<T>(cur.info, c));   // {R[s], NaN if s terminal else 0}
-            const T rs = rp.x;
-            T ra[4], m = T(0);
-            if constexpr (TIES) {
-              const T rts = cur.rt[c];
-              ra[0] = (inf & kBlkU) ? rts : up.rt[c];
-              ra[1] = (inf & kBlkR) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
-              ra[2] = (inf & kBlkD) ? rts : dn.rt[c];
-              ra[3] = (inf & kBlkL) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
-              // terminal rows are all zero (utils.py:70): NaN never compares equal
-              m = N::add(max_nn(max_nn(ra[0], ra[1]), max_nn(ra[2], ra[3])), rp.y);
-            }
-            if constexpr (WRITE_TIE) {
-              const uint32_t mk = (ra[0] == m ? 1u : 0u) | (ra[1] == m ? 2u : 0u) | (ra[2] == m ? 4u : 0u) |
-                                  (ra[3] == m ? 8u : 0u);
-              ties[c >> 2] |= mk << (8 * (c & 3));
-            } else if constexpr (KIND == GU_POLICY_GREEDY) {
-              out[c] = backup_ties(rs, ra, m, ga, luts);
-            } else if constexpr (KIND == GU_POLICY_PROBS) {
-              const uint4* mine = &pstage[((threadIdx.x >> 5) * 2 + ((ry - ry0) & 1)) * kStage + lane * (UPT + 1)];
-              T pp[4];
-              if constexpr (sizeof(T) == 4) {
-                const float4 f = *reinterpret_cast<const float4*>(mine + c);
-                pp[0] = f.x; pp[1] = f.y; pp[2] = f.z; pp[3] = f.w;
-              } else {
-                const double2 d0 = *reinterpret_cast<const double2*>(mine + 2 * c);
-                const double2 d1 = *reinterpret_cast<const double2*>(mine + 2 * c + 1);
-                pp[0] = d0.x; pp[1] = d0.y; pp[2] = d1.x; pp[3] = d1.y;
+            for (int c = 0; c < CPT; c += 2) {
+              float ga[2][4], ra[2][4], m[2];
+              uint32_t off[2];
+#pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int cc = c + k;
+                const uint32_t inf = info_of(cur.info, cc);
+                const float gs = cur.g[cc], rts = cur.rt[cc];
+                ga[k][0] = (inf & kBlkU) ? gs : up.g[cc];
+                ga[k][1] = (inf & kBlkR) ? gs : (cc == CPT - 1 ? cur.gr : cur.g[cc + 1 < CPT ? cc + 1 : cc]);
+                ga[k][2] = (inf & kBlkD) ? gs : dn.g[cc];
+                ga[k][3] = (inf & kBlkL) ? gs : (cc == 0 ? cur.gl : cur.g[cc > 0 ? cc - 1 : cc]);
+                ra[k][0] = (inf & kBlkU) ? rts : up.rt[cc];
+                ra[k][1] = (inf & kBlkR) ? rts : (cc == CPT - 1 ? cur.rtr : cur.rt[cc + 1 < CPT ? cc + 1 : cc]);
+                ra[k][2] = (inf & kBlkD) ? rts : dn.rt[cc];
+                ra[k][3] = (inf & kBlkL) ? rts : (cc == 0 ? cur.rtl : cur.rt[cc > 0 ? cc - 1 : cc]);
+                m[k] = max_nn(max_nn(ra[k][0], ra[k][1]), max_nn(ra[k][2], ra[k][3]));
+                off[k] = lut_offset<T>(cur.info, cc);
               }
-              T acc = rs;
+              float o0, o1;
+              backup_ties_pair(ra[0], ra[1], m[0], m[1], ga[0], ga[1], off[0], off[1], luts, o0, o1);
+              out[c] = o0;
+              out[c + 1] = o1;
+            }
+          } else {
 #pragma unroll
-              for (int a = 0; a < 4; ++a) acc = N::add(acc, N::mul(pp[a], ga[a]));
-              out[c] = acc;
-            } else {
-              const uint32_t mk = KIND == GU_POLICY_UNIFORM ? 15u : (pm[c >> 2] >> (8 * (c & 3))) & 15u;
-              const T p = KIND == GU_POLICY_UNIFORM ? T(0.25) : luts.inv_cnt[__popc(mk)];
-              T acc = rs;
-#pragma unroll
-              for (int a = 0; a < 4; ++a)
-                if ((mk >> a) & 1u) acc = N::add(acc, N::mul(p, ga[a]));
-              out[c] = acc;
+            for (int c = 0; c < CPT; ++c) {
+              const uint32_t inf = info_of(cur.info, c);
+              const T gs = cur.g[c];
+              // discounted value of the landing cell per action: UP, RIGHT, DOWN, LEFT
+              T ga[4];
+              ga[0] = (inf & kBlkU) ? gs : up.g[c];
+              ga[1] = (inf & kBlkR) ? gs : (c == CPT - 1 ? cur.gr : cur.g[c + 1 < CPT ? c + 1 : c]);
+              ga[2] = (inf & kBlkD) ? gs : dn.g[c];
+              ga[3] = (inf & kBlkL) ? gs : (c == 0 ? cur.gl : cur.g[c > 0 ? c - 1 : c]);
+              const auto rp = reward_poison_at(luts, lut_offset<T>(cur.info, c));   // {R[s], NaN if s terminal else 0}
+              const T rs = rp.x;
+              T ra[4], m = T(0);
+              if constexpr (TIES) {
+                const T rts = cur.rt[c];
+                ra[0] = (inf & kBlkU) ? rts : up.rt[c];
+                ra[1] = (inf & kBlkR) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
+                ra[2] = (inf & kBlkD) ? rts : dn.rt[c];
+                ra[3] = (inf & kBlkL) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
+                // terminal rows are all zero (utils.py:70): NaN never compares equal
+                m = N::add(max_nn(max_nn(ra[0], ra[1]), max_nn(ra[2], ra[3])), rp.y);
+              }
+              if constexpr (WRITE_TIE) {
+                const uint32_t mk = (ra[0] == m ? 1u : 0u) | (ra[1] == m ? 2u : 0u) | (ra[2] == m ? 4u : 0u) |
+                                    (ra[3] == m ? 8u : 0u);
+                ties[c >> 2] |= mk << (8 * (c & 3));
+              } else if constexpr (KIND == GU_POLICY_GREEDY) {
+                out[c] = backup_ties(rs, ra, m, ga, luts);
+              } else if constexpr (KIND == GU_POLICY_PROBS) {
+                const uint4* mine = &pstage[((threadIdx.x >> 5) * 2 + ((ry - ry0) & 1)) * kStage + lane * (UPT + 1)];
+                T pp[4];
+                if constexpr (sizeof(T) == 4) {
+                  const float4 f = *reinterpret_cast<const float4*>(mine + c);
+                  pp[0] = f.x; pp[1] = f.y; pp[2] = f.z; pp[3] = f.w;
+                } else {
+                  const double2 d0 = *reinterpret_cast<const double2*>(mine + 2 * c);
+                  const double2 d1 = *reinterpret_cast<const double2*>(mine + 2 * c + 1);
+                  pp[0] = d0.x; pp[1] = d0.y; pp[2] = d1.x; pp[3] = d1.y;
+                }
+                T acc = rs;
+  #pragma unroll
+                for (int a = 0; a < 4; ++a) acc = N::add(acc, N::mul(pp[a], ga[a]));
+                out[c] = acc;
+              } else {
+                const uint32_t mk = KIND == GU_POLICY_UNIFORM ? 15u : (pm[c >> 2] >> (8 * (c & 3))) & 15u;
+                const T p = KIND == GU_POLICY_UNIFORM ? T(0.25) : luts.inv_cnt[__popc(mk)];
+                T acc = rs;
+  #pragma unroll
+                for (int a = 0; a < 4; ++a)
+                  if ((mk >> a) & 1u) acc = N::add(acc, N::mul(p, ga[a]));
+                out[c] = acc;
+              }
             }
           }
           if constexpr (WRITE_TIE) {
@@ -576,10 +709,20 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               for (int k = 0; k < IW; ++k) *reinterpret_cast<uint32_t*>(tie_out + o + 4 * k) = ties[k];
             }
           } else {
-            if (full) {
+            if constexpr (kPack) {
+              if (full) {
+#pragma unroll
+                for (int c = 0; c < CPT; c += 2) {      // v - out = fma(out, -1, v): one rounding, like the scalar subtract
+                  const float2 d = __ffma2_rn(make_float2(out[c], out[c + 1]), make_float2(-1.0f, -1.0f),
+                                              make_float2(cur.v[c], cur.v[c + 1]));
+                  dmax = max_nn(max_nn(dmax, d.x), d.y);
+                }
+              }
+            } else if (full) {
 #pragma unroll
               for (int c = 0; c < CPT; ++c) dmax = max_nn(dmax, N::add(cur.v[c], -out[c]));
-            } else {
+            }
+            if (!full) {
 #pragma unroll
               for (int c = 0; c < CPT; ++c)
                 if (x0 + c < g.X) dmax = max_nn(dmax, N::add(cur.v[c], -out[c]));
