@@ -387,11 +387,19 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
 }
 
+// Resident blocks per SM the register allocation is held to.  The fp32 fused-greedy sweep needs ~160
+// registers (three window rows of v / g / rt for 8 cells + the packed backup of a cell pair): 3 blocks
+// x 4 warps without spills measured 0.480 ms at 16384^2 against 0.550 ms for 4 blocks with spills; the
+// other fp32 kinds fit 128 registers (4 blocks); fp64 is left to the compiler (2 blocks).
 #ifndef GU_TILED_MIN_BLOCKS
-#define GU_TILED_MIN_BLOCKS 3       // fp32: 3 blocks x 4 warps per SM, up to 168 registers per thread (no spills)
+#define GU_TILED_MIN_BLOCKS 3
 #endif
+template <typename T, int KIND, bool WRITE_TIE>
+constexpr int tiled_min_blocks() {
+  return sizeof(T) != 4 ? 1 : ((KIND == GU_POLICY_GREEDY && !WRITE_TIE) ? GU_TILED_MIN_BLOCKS : 4);
+}
 template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false>
-__global__ void __launch_bounds__(kTiledWarps * 32, (sizeof(T) == 4 ? GU_TILED_MIN_BLOCKS : 1))
+__global__ void __launch_bounds__(kTiledWarps * 32, (tiled_min_blocks<T, KIND, WRITE_TIE>()))
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
                    T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block,
