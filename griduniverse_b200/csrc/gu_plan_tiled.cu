@@ -339,47 +339,61 @@ __device__ __forceinline__ void peer_publish(const PeerArgs<T>& p, int slot, T v
   __threadfence_system();
 }
 
-// max over all ranks of slot `slot` of the local table, spinning until every entry has arrived.
-// false = aborted (this rank's wait timed out, or another rank raised the abort word).
+// Outcome of a wait: the value / flag arrived, the solve was aborted (this rank's wait timed out or
+// another rank raised the abort word), or the sticky stop word is set.  After convergence the rows
+// and flags of the gated-off sweeps never arrive, so every spin also polls the stop word.
+enum { kWaitOk = 0, kWaitAborted = 1, kWaitStopped = 2 };
+
+template <bool POLL_STOP, typename T, typename Cond>
+__device__ __forceinline__ int peer_spin(const PeerArgs<T>& p, Cond arrived) {
+  if (arrived()) return kWaitOk;
+  const long long t0 = clock64();
+  do {
+    if (POLL_STOP && *reinterpret_cast<const volatile int*>(p.stop) != 0) return kWaitStopped;
+    if (peer_aborted(p)) return kWaitAborted;
+    if (clock64() - t0 > p.timeout) { peer_abort(p); return kWaitAborted; }
+  } while (!arrived());
+  return kWaitOk;
+}
+
+// one entry of slot `slot` of the local table (spins until rank r has reported; NaN = not yet)
+template <bool POLL_STOP = true, typename T>
+__device__ __forceinline__ int peer_wait_entry(const PeerArgs<T>& p, int slot, int r, T& out) {
+  const volatile T* e = p.tables[p.rank] + static_cast<size_t>(slot) * p.world + r;
+  T v = Num<T>::neg_inf();
+  const int rc = peer_spin<POLL_STOP>(p, [&]() { v = *e; return v == v; });
+  out = rc == kWaitOk ? v : Num<T>::neg_inf();
+  return rc;
+}
+
+// spin until *word >= target (a neighbour's halo flag)
+template <bool POLL_STOP = true, typename T>
+__device__ __forceinline__ int peer_wait_flag(const PeerArgs<T>& p, const int* word, int target) {
+  const volatile int* w = word;
+  return peer_spin<POLL_STOP>(p, [&]() { return *w >= target; });
+}
+
+// all entries of a slot (the host-side wait kernel, which waits whatever the stop word says): max
+// over ranks, or false if aborted
 template <typename T>
 __device__ __forceinline__ bool peer_wait_slot(const PeerArgs<T>& p, int slot, T& out) {
-  const volatile T* tab = p.tables[p.rank] + static_cast<size_t>(slot) * p.world;
   T m = Num<T>::neg_inf();
-  long long t0 = 0;
   for (int r = 0; r < p.world; ++r) {
-    T v = tab[r];
-    while (v != v) {                              // NaN = not written yet
-      if (t0 == 0) t0 = clock64();
-      if (peer_aborted(p)) return false;
-      if (clock64() - t0 > p.timeout) { peer_abort(p); return false; }
-      v = tab[r];
-    }
+    T v;
+    if (peer_wait_entry<false>(p, slot, r, v) != kWaitOk) return false;
     m = v > m ? v : m;
   }
   out = m;
   return true;
 }
 
-// spin until *word >= target (a neighbour's halo flag)
 template <typename T>
-__device__ __forceinline__ bool peer_wait_flag(const PeerArgs<T>& p, const int* word, int target) {
-  const volatile int* w = word;
-  if (*w >= target) return true;
-  const long long t0 = clock64();
-  while (*w < target) {
-    if (peer_aborted(p)) return false;
-    if (clock64() - t0 > p.timeout) { peer_abort(p); return false; }
-  }
-  return true;
-}
-
-template <typename T>
-__global__ void peer_wait_kernel(PeerArgs<T> p) {
+__global__ void peer_wait_kernel(const __grid_constant__ PeerArgs<T> p) {
   const int slot = p.slot + (p.slot_base ? *p.slot_base : 0);
   T m;
   if (!peer_wait_slot(p, slot, m)) return;
-  if (p.up_flag && !peer_wait_flag(p, p.halo + 0, slot + 1)) return;
-  if (p.down_flag && !peer_wait_flag(p, p.halo + 1, slot + 1)) return;
+  if (p.up_flag && peer_wait_flag<false>(p, p.halo + 0, slot + 1) != kWaitOk) return;
+  if (p.down_flag && peer_wait_flag<false>(p, p.halo + 1, slot + 1) != kWaitOk) return;
   __threadfence_system();
 }
 
@@ -403,7 +417,9 @@ __global__ void __launch_bounds__(kTiledWarps * 32, (tiled_min_blocks<T, KIND, W
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
                    T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block,
-                   PeerArgs<T> peer = PeerArgs<T>()) {
+                   const __grid_constant__ PeerArgs<T> peer) {   // read in place from the constant bank: the
+                                                                 // helpers take it by reference, and a by-value
+                                                                 // copy would be spilled to local memory by every thread
   using N = Num<T>;
   using V = typename Vec<T>::type;
   constexpr int W = Vec<T>::W;
@@ -435,24 +451,30 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
     bot_edge = by == nby - 1 && peer.down_flag != nullptr;
     slot = peer.slot + (peer.slot_base != nullptr ? *peer.slot_base : 0);
     __shared__ int go_sh;
-    if (threadIdx.x == 0) {
-      int go = 1;
-      if (peer_aborted(peer) || *reinterpret_cast<const volatile int*>(peer.stop) != 0) {
-        go = 0;
-      } else {
-        const int gslot = slot - peer.lag;
-        if (gslot >= peer.first_slot) {
-          T m;
-          if (!peer_wait_slot(peer, gslot, m)) go = 0;
-          else if (m < peer.thr) { *reinterpret_cast<volatile int*>(peer.stop) = 1; go = 0; }   // converged earlier: keep V
-        }
-        if (go && slot > peer.first_slot) {
-          if (top_edge && !peer_wait_flag(peer, peer.halo + 0, slot)) go = 0;
-          if (go && bot_edge && !peer_wait_flag(peer, peer.halo + 1, slot)) go = 0;
-          if (top_edge || bot_edge) __threadfence_system();     // acquire the neighbour's rows
-        }
+    if (threadIdx.x < 32) {
+      // one warp, one round trip in the common case: lane r < world reads rank r's entry of the gate
+      // row, lanes 31 / 30 the sticky stop and the abort word, lanes 29 / 28 the halo flags
+      const int lane0 = threadIdx.x;
+      const int gslot = slot - peer.lag;
+      int bad = 0;                                   // non-zero: stop (converged earlier / aborted)
+      T v = N::neg_inf();
+      if (lane0 == 31) bad = *reinterpret_cast<const volatile int*>(peer.stop) != 0;
+      if (lane0 == 30) bad = peer_aborted(peer);
+      if (gslot >= peer.first_slot && lane0 < peer.world) bad = peer_wait_entry(peer, gslot, lane0, v);
+      if (slot > peer.first_slot) {
+        if (lane0 == 29 && top_edge) bad = peer_wait_flag(peer, peer.halo + 0, slot);
+        if (lane0 == 28 && bot_edge) bad = peer_wait_flag(peer, peer.halo + 1, slot);
       }
-      go_sh = go;
+      const bool any_bad = __any_sync(0xffffffffu, bad != 0);
+      const T m = warp_max(v);
+      int go = 1;
+      if (any_bad) go = 0;
+      else if (gslot >= peer.first_slot && m < peer.thr) {     // converged earlier: keep V
+        if (lane0 == 0) *reinterpret_cast<volatile int*>(peer.stop) = 1;
+        go = 0;
+      }
+      if (go && (top_edge || bot_edge)) __threadfence_system();     // acquire the neighbour's rows
+      if (lane0 == 0) go_sh = go;
     }
     __syncthreads();
     if (!go_sh) return;
@@ -955,7 +977,8 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
   const uint8_t* info = g->info;
 #define GU_LAUNCH(KIND)                                                                                   \
   sweep_tiled_kernel<T, KIND, WRITE_TIE, NV><<<grid, kTiledWarps * 32, 0, st>>>(v, info, vin, vout, tie, policy, \
-                                                                           gamma, residual, gate, gate_thr, rpb)
+                                                                           gamma, residual, gate, gate_thr, rpb, \
+                                                                           PeerArgs<T>())
   if (WRITE_TIE) {
     GU_LAUNCH(GU_POLICY_GREEDY);
   } else {
