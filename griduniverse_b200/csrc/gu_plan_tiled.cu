@@ -444,9 +444,14 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   if (!PEER) {
     if (gate != nullptr && *gate < gate_thr) return;
   } else {
-    // the two edge block rows are scheduled first: their rows travel while the interior computes
     const int nby = gridDim.y;
+    // (Scheduling the last block row second, so that its rows travel while the interior computes, was
+    // measured at +23 % kernel time on one GPU -- 0.320 against 0.260 ms at 8192 rows -- for reasons the
+    // instruction mix does not explain; with the natural order the only exposed latency is one NVLink
+    // store + flag at the start of the neighbour's next sweep, in its first 16 blocks.)
+#ifdef GU_PEER_REMAP
     if (nby >= 3) by = blockIdx.y == 0 ? 0 : (blockIdx.y == 1 ? nby - 1 : static_cast<int>(blockIdx.y) - 1);
+#endif
     top_edge = by == 0 && peer.up_flag != nullptr;
     bot_edge = by == nby - 1 && peer.down_flag != nullptr;
     slot = peer.slot + (peer.slot_base != nullptr ? *peer.slot_base : 0);
@@ -759,18 +764,26 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             }
 #pragma unroll
             for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(vout + o + k * W) = pack(out + k * W);
-            if (PEER) {
-              if (ry == 0 && peer.up_ghost != nullptr) {
-#pragma unroll
-                for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(peer.up_ghost + x0 + k * W) = pack(out + k * W);
-              }
-              if (ry == rows - 1 && peer.down_ghost != nullptr) {
-#pragma unroll
-                for (int k = 0; k < NV; ++k) *reinterpret_cast<V*>(peer.down_ghost + x0 + k * W) = pack(out + k * W);
-              }
-            }
           }
         }
+      }
+    }
+  }
+  if constexpr (PEER && !WRITE_TIE) {
+    // The shard's first / last output row also goes into the neighbour's ghost row (peer memory over
+    // NVLink).  Done after the row loop -- each thread reads back the vectors it has just stored -- so
+    // the loop itself carries no peer code (inside it the two per-row tests cost 27 % at 8192 rows).
+    if (active && (top_edge || bot_edge)) {
+      if (top_edge) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          *reinterpret_cast<V*>(peer.up_ghost + x0 + k * W) = *reinterpret_cast<const V*>(vout + pitch + x0 + k * W);
+      }
+      if (bot_edge) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k)
+          *reinterpret_cast<V*>(peer.down_ghost + x0 + k * W) =
+              *reinterpret_cast<const V*>(vout + rows * pitch + x0 + k * W);
       }
     }
   }
@@ -799,6 +812,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
 #pragma unroll
         for (int k = 1; k < kTiledWarps; ++k) m = scratch[k] > m ? scratch[k] : m;
         atomic_max_signed(residual, m);
+#ifndef GU_PEER_NO_DONE
         if (PEER) {
           __threadfence();
           const int nblocks = gridDim.x * gridDim.y;
@@ -809,6 +823,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
             peer_publish(peer, slot, fin);
           }
         }
+#endif
       }
     }
   }
@@ -879,8 +894,10 @@ template <> struct TiledNV<double> { static constexpr int value = GU_TILED_NV_F6
 template <typename K>
 static int choose_rows_per_block(K kernel, int rows, int blocks_x) {
   const int def = GU_TILED_ROWS_PER_BLOCK;
-  static const char* fixed = getenv("GU_TILED_FIXED_RPB");   // developer switch for A/B timing
+  static const char* fixed = getenv("GU_TILED_FIXED_RPB");   // developer switches for A/B timing
   if (fixed) return def;
+  static const char* force = getenv("GU_TILED_RPB");
+  if (force && atoi(force) > 0) return atoi(force);
   static int sms = 0;
   if (!sms) {
     int dev = 0;

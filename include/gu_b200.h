@@ -217,7 +217,6 @@ int gu_sweep_f32(const gu_grid* g, const float* v_in, float* v_out, int policy_k
  *     Only the first / last block row of sweep slot >= 1 waits, and only for its own neighbour:
  *     halo_flags[0] >= slot (rows from above have arrived, and the neighbour above has finished
  *     reading the ghost row this sweep is about to overwrite), halo_flags[1] >= slot likewise.
- *     Those blocks are scheduled first, so the rows travel while the interior is computed.
  *   residual / stopping rule   when the last block of the shard finishes, max(v_in - v_out) of the
  *     shard goes to entry [slot][rank] of EVERY rank's residual table res_tables[r]
  *     (T[n_slots][world], NaN = not written yet; res_tables[rank] is this rank's own).  Sweep `slot`

@@ -31,7 +31,7 @@ k = [0]
 
 
 def peer():
-    svi._sweep_peer(k[0], 0, 3, None, 0.9, -1.0, 0)
+    svi._sweep_peer(k[0], 0, 3, None, 0.9, -1.0, int(os.environ.get('FIRST', '0')))
     k[0] += 1
 
 
