@@ -41,6 +41,9 @@ VI_SIZE = 16384
 VI_GAMMA, VI_THETA = 0.9, 1e-6
 BYTES_PER_STEP_SUMMARY = 4.0          # int32 action per env step, summaries only
 BYTES_PER_CELL_FUSED_F32 = 8.375      # read V + write V' + 3 mask bits
+TRAFFIC_NOTE = ("profiled constant: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed "
+                "ncu --set full capture (profiles/traffic.json), scaled to this launch's share of the units; "
+                "not measured in this run (a run under ncu is never a bench number)")
 
 
 def measured_peak():
@@ -147,6 +150,7 @@ def run_reference(args):
                "cpu_baseline": {"value": vi["value"], "unit": "cell-updates/s", "cores": procs, "kind": "port",
                                 "sample": "%d replicas of a 512x512 synthetic maze, 4 sweep+greedy iterations "
                                           "each, fp32 oracle" % procs}},
+        "cpu_reference": reference_cpu_numbers(),
     }
     emit(line)
 
@@ -155,7 +159,9 @@ def env_config(n_gpus):
     return {"workload": "cfg4: 16,777,216 independent 8x8 envs (per-env walls/lava/goal bit planes), "
                         "T=256 int32 actions per env per pass, auto-reset, summaries only",
             "envs_total": ENV_TOTAL, "grid": "8x8", "steps_per_pass": ENV_T, "parallelism": "env-sharded x%d, no collective" % n_gpus,
-            "l2": "inputs larger than L2 (%.1f GB of actions per GPU per pass)" % (ENV_TOTAL / n_gpus * ENV_T * 4 / 1e9)}
+            "l2": "inputs larger than L2 (%.1f GB of actions per GPU per pass)" % (ENV_TOTAL / n_gpus * ENV_T * 4 / 1e9),
+            "cpu_arm": "the CPU arm times a bounded 1/128-size sample of this workload (one process per host core x "
+                       "32,768 envs x 64 steps, same generator) and reports its rate"}
 
 
 # ----------------------------------------------------------------------------------------
@@ -331,11 +337,27 @@ def run_ours(args):
     vi_e2e_value = io["sweeps"] * cells / t_vi_e2e
     clocks = sampler.stop() if sampler else None
 
+    # ------------------------------------------------------------------ policy iteration on cfg 5
+    # dynamic_programming.py:31-57 with the reference's default step budget (max_steps = 1000): on this
+    # grid one evaluation phase needs ~130 sweeps, so the budget ends mid-evaluation and the solve is a
+    # fixed 1000 sweeps + one greedy extraction per converged phase + the exhaustion branch (:48-56).
+    PI_STEPS = 1000
+    pi_meta = {}
+
+    def pi_pass():
+        v, tie, n, d_eval, exhausted = svi.policy_iteration("uniform", None, VI_THETA, PI_STEPS, VI_GAMMA, chunk=16)
+        pi_meta.update(sweeps=n, delta_eval=d_eval, exhausted=bool(exhausted), v=v, tie=tie)
+
+    pi_pass()
+    t_pi = timed(pi_pass, 1)
+    pi_value = pi_meta["sweeps"] * cells / t_pi
+
     # ------------------------------------------------------------------ cfg-5 parity record
     # north_star cfg 5 (i): the sharded result is bit-identical to the single-GPU result.  Every rank
     # also solves the WHOLE grid on its own GPU and compares its rows of V and of the tie masks byte
-    # for byte with what each multi-GPU driver produced; the digest is a checksum of per-2048-row
-    # checksums, so it is the same number at every N.
+    # for byte with what each multi-GPU driver produced (value iteration: both drivers; policy
+    # iteration: the default driver); the digest is a checksum of per-2048-row checksums, so it is the
+    # same number at every N.
     import hashlib
 
     def block_digests(t, first_row):
@@ -354,36 +376,56 @@ def run_ours(args):
             mine = torch.cat(parts)
         return hashlib.sha256(bytes(mine.cpu().numpy().tobytes())).hexdigest()
 
+    def own(t):
+        return t[1:-1, :VI_SIZE]
+
+    pi_parity = {"ranks": world, "sweeps": pi_meta["sweeps"], "exhausted": pi_meta["exhausted"],
+                 "sha256_V": combined(block_digests(own(pi_meta["v"]), r0)),
+                 "sha256_ties": combined(block_digests(own(pi_meta["tie"]), r0))}
+    pi_own = (own(pi_meta["v"]).clone(), own(pi_meta["tie"]).clone(), pi_meta["sweeps"])
     v_s, tie_s, sw_s, _ = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
-    own_v, own_t = v_s[1:-1, :VI_SIZE], tie_s[1:-1, :VI_SIZE]
-    parity = {"ranks": world, "sweeps": sw_s, "sha256_V": combined(block_digests(own_v, r0)),
-              "sha256_ties": combined(block_digests(own_t, r0)),
+    parity = {"ranks": world, "sweeps": sw_s, "sha256_V": combined(block_digests(own(v_s), r0)),
+              "sha256_ties": combined(block_digests(own(tie_s), r0)),
               "how": "sha256 over the sha256 of every 2048-row block of V (f32 bytes) / of the tie masks"}
     if world > 1:
-        drivers = {("peer" if isinstance(svi, PeerValueIteration) else "nccl"): (own_v, own_t, sw_s)}
+        drivers = {("peer" if isinstance(svi, PeerValueIteration) else "nccl"): (own(v_s), own(tie_s), sw_s)}
         if isinstance(svi, PeerValueIteration):                     # the NCCL-driven arm as well
             svi2 = ShardedValueIteration(pl)
             v2, t2, sw2, _ = svi2.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
-            drivers["nccl"] = (v2[1:-1, :VI_SIZE], t2[1:-1, :VI_SIZE], sw2)
+            drivers["nccl"] = (own(v2), own(t2), sw2)
         full = synth.maze_plan_grid(VI_SIZE, VI_SIZE, seed=0, dtype=np.float32, device=dev)
         solo = ShardedValueIteration(Planner(None, np.float32, dev, grid=full), solo=True)
-        v1, t1, sw1, _ = solo.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
-        verdicts = {}
-        for name, (dv, dtie, dsw) in sorted(drivers.items()):
+
+        def same_as_solo(dv, dtie, dsw, v1, t1, sw1):
             same = (dsw == sw1 and torch.equal(dv, v1[1 + r0:1 + r1, :VI_SIZE])
                     and torch.equal(dtie, t1[1 + r0:1 + r1, :VI_SIZE]))
             flag = torch.tensor([1 if same else 0], dtype=torch.int32, device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            verdicts[name] = bool(flag.item())
+            return bool(flag.item())
+
+        v1, t1, sw1, _ = solo.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
+        verdicts = {name: same_as_solo(dv, dtie, dsw, v1, t1, sw1) for name, (dv, dtie, dsw) in sorted(drivers.items())}
         parity["drivers"] = verdicts
         parity["bit_identical"] = all(verdicts.values())
         parity["against"] = "a solo solve of the whole 16384x16384 grid on every rank's own GPU"
         if rank == 0:      # the single-GPU digest, computed from rank 0's solo solve: must equal sha256_V
-            parity["sha256_V_single_gpu"] = hashlib.sha256(b"".join(block_digests(v1[1:-1, :VI_SIZE], 0))).hexdigest()
-        del full, solo, v1, t1
+            parity["sha256_V_single_gpu"] = hashlib.sha256(b"".join(block_digests(own(v1), 0))).hexdigest()
+        del v1, t1
+        p1, pt1, psw1, _, _ = solo.policy_iteration("uniform", None, VI_THETA, PI_STEPS, VI_GAMMA, chunk=16)
+        pi_parity["bit_identical"] = same_as_solo(pi_own[0], pi_own[1], pi_own[2], p1, pt1, psw1)
+        pi_parity["against"] = parity["against"]
+        del full, solo, p1, pt1
     else:
         parity["bit_identical"] = None     # N = 1 is the reference point: compare sha256_V across runs
+        pi_parity["bit_identical"] = None
+    del pi_own
+    pi_meta.pop("v"), pi_meta.pop("tie")
     torch.cuda.empty_cache()
+
+    # ------------------------------------------------------------------ small configurations (rank 0)
+    cfg1 = cfg2 = None
+    if rank == 0:
+        cfg1, cfg2 = small_configs(dev, world)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu_env = cpu_vi = None
@@ -405,6 +447,7 @@ def run_ours(args):
             "config": env_config(world),
             "roofline": {"bound": "hbm", "achieved": env_achieved, "peak": peak, "unit": "GB/s",
                          "frac": env_achieved / peak, "traffic": profiled_traffic("rollout_cfg4", n_local / float(ENV_TOTAL)),
+                         "traffic_source": TRAFFIC_NOTE,
                          "kernel": "rollout (gu_rollout), 4 B/step x %d envs x %d steps per launch" % (n_local, ENV_T),
                          "peak_source": peak_src},
             "e2e": {"value": env_e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_io["h2d"] * world,
@@ -423,6 +466,7 @@ def run_ours(args):
                            "l2": "inputs larger than L2 (%.2f GB of V per GPU)" % ((r1 - r0) * VI_SIZE * 4 / 1e9)},
                 "roofline": {"bound": "hbm", "achieved": vi_achieved, "peak": peak, "unit": "GB/s",
                              "frac": vi_achieved / peak, "traffic": profiled_traffic("sweep_greedy_f32_cfg5", (r1 - r0) / float(VI_SIZE)),
+                             "traffic_source": TRAFFIC_NOTE,
                              "kernel": "fused-greedy sweep (gu_sweep_f32, GU_POLICY_GREEDY), 8.375 B/cell",
                              "ms_per_launch": 1000.0 * t_sw, "peak_source": peak_src},
                 "e2e": {"value": vi_e2e_value, "unit": "cell-updates/s", "h2d_bytes_per_step": io["h2d"] * world,
@@ -430,11 +474,139 @@ def run_ours(args):
                 "gpu_launches": vi_launches, "collectives": vi_colls, "cpu_baseline": cpu_vi,
                 "parity": parity,
             },
+            "pi": {"metric": "pi_cell_updates_per_sec", "value": pi_value, "unit": "cell-updates/s", "dtype": "f32",
+                   "sweeps_per_solve": pi_meta["sweeps"], "ms_per_solve": 1000.0 * t_pi, "exhausted": pi_meta["exhausted"],
+                   "config": {"workload": "cfg5 grid: policy_iteration (dynamic_programming.py:31-57), gamma 0.9, theta 1e-6, "
+                                          "uniform policy0, V0=0, max_steps=1000 (the reference default)",
+                              "parallelism": "row-sharded x%d, same driver as vi" % world},
+                   "parity": pi_parity},
+            "cfg1": cfg1, "cfg2": cfg2,
             "cfg3": cfg3,
         }
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def reference_cpu_numbers():
+    """The UNMODIFIED reference timed on this box's host cores when its tree is present
+    (oracle/ref_timing.py), else the committed numbers from the authoring container, labelled."""
+    try:
+        from oracle import ref_timing
+        if ref_timing.available():
+            r = ref_timing.time_reference()
+            r["where"] = "this box, this run (%d host cores, the reference is single-threaded)" % (os.cpu_count() or 1)
+            return r
+    except Exception as e:      # noqa: BLE001 - a baseline must never take the bench down
+        sys.stderr.write("reference timing failed: %r\n" % (e,))
+    p = os.path.join(ROOT, "profiles", "r2_reference_cpu.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            r = json.load(f)
+        r["where"] = ("authoring container, committed in profiles/r2_reference_cpu.json: the Python reference "
+                      "tree does not exist on the GPU box")
+        return r
+    return {"unavailable": "no reference tree on this box and no committed timing"}
+
+
+def small_configs(dev, world):
+    """BASELINE cfg 1 and cfg 2 through the reference-signature API (latency-bound, one GPU), the
+    batched form of cfg 2 (one launch, one thread block per maze), and the CPU arms beside them."""
+    import torch
+    import warnings as _w
+    import griduniverse_b200.algorithms.dynamic_programming as dp
+    from griduniverse_b200.batch import MazeBatch
+    from griduniverse_b200.envs import GridUniverseEnv
+    from oracle import gu_oracle as orc
+    ref = reference_cpu_numbers() if world == 1 else None
+    with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:
+        levels = json.load(f)
+    golden = np.load(os.path.join(ROOT, "tests", "golden", "golden.npz"))
+
+    def wall(fn, n):
+        fn()
+        torch.cuda.synchronize()
+        t = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t) / n
+
+    # cfg 1: GridUniverseEnv() 4x4, 1000 host-supplied random actions, reset on done
+    env = GridUniverseEnv()
+    acts = np.random.RandomState(0).randint(0, 4, 1000)
+    traj = []
+
+    def loop(record=None):
+        env.reset()
+        for a in acts:
+            o, r, done, _ = env.step(int(a))
+            if record is not None:
+                record.append((o, int(r), bool(done)))
+            if done:
+                env.reset()
+
+    loop(traj)
+    olv = orc.Level(4, 4)
+    pos, otraj = 0, []
+    for a in acts:                                   # the same loop on the oracle (parity + CPU port timing)
+        pos, r, d = orc.look_step_ahead(olv, pos, int(a))
+        otraj.append((pos, int(r), bool(d)))
+        if d:
+            pos = 0
+    t_port = time.perf_counter()
+    for _ in range(5):
+        pos = 0
+        for a in acts:
+            pos, r, d = orc.look_step_ahead(olv, pos, int(a))
+            if d:
+                pos = 0
+    t_port = (time.perf_counter() - t_port) / 5000
+    cfg1 = {"workload": "cfg1: default 4x4 GridUniverseEnv, 1 env, 1000 host-supplied random actions, reset on done, "
+                        "through GridUniverseEnv.step (one launch + one stream sync per step: latency-bound)",
+            "us_per_step": wall(loop, 3) / 1000 * 1e6, "gpu_launches_per_step": 1,
+            "bit_exact_vs_oracle": traj == otraj,
+            "cpu_port_us_per_step": t_port * 1e6,
+            "cpu_reference_us_per_step": (ref or {}).get("cfg1", {}).get("us_per_step"),
+            "note": "one env is not a data-parallel workload: the reference's interpreter loop is faster per step "
+                    "than a kernel launch; the batched path is the headline line"}
+
+    # cfg 2: 10x10 reference-generated maze, gamma 0.9, theta 1e-6: single solves, then a batch
+    lvl = GridUniverseEnv.from_text_lines(levels["gen10_0"])
+    N = lvl.world.size
+    cfg2 = {"workload": "cfg2: value_iteration + policy_iteration on a 10x10 generated maze, gamma 0.9, theta 1e-6, "
+                        "fp64 (bit-exact mode)"}
+    for name, fn in (("value_iteration", dp.value_iteration), ("policy_iteration", dp.policy_iteration)):
+        def solve():
+            with _w.catch_warnings():
+                _w.simplefilter("ignore")
+                return fn(np.ones((N, 4)) / 4, lvl, np.zeros(N), threshold=1e-6, max_steps=1000, discount_factor=0.9)
+        V, P = solve()
+        key = "vi" if name == "value_iteration" else "pi"
+        cfg2[name] = {"ms_per_solve": wall(solve, 5) * 1e3, "sweeps": fn.last_sweeps, "gpu_launches": 1,
+                      "bit_exact_vs_reference_golden": V.tobytes() == golden["%s/gen10_0/V" % key].tobytes(),
+                      "cpu_reference_ms_per_solve": (ref or {}).get("cfg2", {}).get(name, {}).get("ms_per_solve")}
+    names = ["gen10_%d" % k for k in range(10)]
+    base = [GridUniverseEnv.from_text_lines(levels[n]).level for n in names]
+    B = 148 * 32
+    mb = MazeBatch([base[i % 10] for i in range(B)], device=dev)
+    V, M, sweeps, _ = mb.value_iteration("uniform", None, 1e-6, 1000, 0.9)
+    ok = all(V[i].cpu().numpy().tobytes() == golden["vi/%s/V" % names[i % 10]].tobytes() for i in range(0, B, 97))
+    t_b = wall(lambda: mb.value_iteration("uniform", None, 1e-6, 1000, 0.9), 5)
+    total_sweeps = float(sweeps.sum().item())
+    Vp, Mp, meta, _ = mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9)
+    okp = all(Vp[i].cpu().numpy().tobytes() == golden["pi/%s/V" % names[i % 10]].tobytes() for i in range(0, B, 97))
+    t_bp = wall(lambda: mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9), 5)
+    cfg2["batched"] = {"workload": "%d mazes (the ten reference-generated 10x10 mazes, tiled) in ONE launch, one thread "
+                                   "block per maze (gu_vi_batch_f64 / gu_pi_batch_f64), results resident on the device" % B,
+                       "mazes": B, "vi_ms_per_launch": t_b * 1e3, "vi_mazes_per_s": B / t_b,
+                       "vi_cell_updates_per_s": total_sweeps * N / t_b, "vi_bit_exact_vs_reference_golden": bool(ok),
+                       "pi_ms_per_launch": t_bp * 1e3, "pi_mazes_per_s": B / t_bp,
+                       "pi_cell_updates_per_s": float(meta[:, 0].sum().item()) * N / t_bp,
+                       "pi_bit_exact_vs_reference_golden": bool(okp)}
+    if ref is not None:
+        cfg2["cpu_reference"] = ref
+    return cfg1, cfg2
 
 
 def run_profile(args):

@@ -21,7 +21,7 @@ GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 
 
 EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
            "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_max_diff_f32", "gu_max_diff_f64", "gu_vi_small_f64",
-           "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_version", "gu_arch", "gu_error_string")
+           "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_vi_batch_f64", "gu_pi_batch_f64", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_version", "gu_arch", "gu_error_string")
 
 
 class GuLevels(ctypes.Structure):
@@ -36,6 +36,13 @@ class GuGrid(ctypes.Structure):
     _fields_ = [("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("row_begin", ctypes.c_int32),
                 ("row_end", ctypes.c_int32), ("pitch", ctypes.c_int32), ("pitch_words", ctypes.c_int32),
                 ("wall", c_ptr), ("goal", c_ptr), ("lava", c_ptr), ("info", c_ptr)]
+
+
+class GuGridBatch(ctypes.Structure):
+    """struct gu_grid_batch (include/gu_b200.h)."""
+    _fields_ = [("X", ctypes.c_int32), ("Y", ctypes.c_int32), ("n_mazes", ctypes.c_int32),
+                ("pitch", ctypes.c_int32), ("pitch_words", ctypes.c_int32), ("cell_stride", ctypes.c_int64),
+                ("plane_stride", ctypes.c_int64), ("wall", c_ptr), ("goal", c_ptr), ("lava", c_ptr)]
 
 
 GU_MAX_PEERS = 16
@@ -79,7 +86,7 @@ def lib():
     L = ctypes.CDLL(path)
     i32, i64, u32, f32, f64, p = (ctypes.c_int32, ctypes.c_int64, ctypes.c_uint32, ctypes.c_float,
                                   ctypes.c_double, c_ptr)
-    lvp, gp = ctypes.POINTER(GuLevels), ctypes.POINTER(GuGrid)
+    lvp, gp, gbp = ctypes.POINTER(GuLevels), ctypes.POINTER(GuGrid), ctypes.POINTER(GuGridBatch)
     sig = {
         "gu_step": (ctypes.c_int, [lvp, i64, p, p, p, p, p, p, p, u32, p]),
         "gu_rollout": (ctypes.c_int, [lvp, i64, i64, p, p, p, p, p, p, p, p, p, p, u32, p]),
@@ -105,6 +112,8 @@ def lib():
         "gu_vi_small_max_cells": (i64, []),
         "gu_pi_small_f64": (ctypes.c_int, [gp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),
         "gu_pi_small_max_cells": (i64, []),
+        "gu_vi_batch_f64": (ctypes.c_int, [gbp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),
+        "gu_pi_batch_f64": (ctypes.c_int, [gbp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),
         "gu_pack_level_text": (ctypes.c_int, [p, i64, i32, i32, p, p, p, p, p, p, p]),
         "gu_render_ansi": (ctypes.c_int, [lvp, i64, p, p, p]),
         "gu_bfs_init": (ctypes.c_int, [gp, p, p, p, p, p, u32, p]),

@@ -125,7 +125,7 @@ __device__ __forceinline__ void gather_cell(const GridView& g, const T* __restri
   const bool goal_s = bit(g.goal, 0, x), lava_s = bit(g.lava, 0, x);
   c.term = goal_s | lava_s;
   c.rs = reward_of(goal_s, lava_s);
-  c.vs = vin[base];
+  c.vs = vin != nullptr ? vin[base] : T(0);      // vin == nullptr: value function of zeros
   c.blk = 0;
   const int dx[4] = {0, 1, 0, -1}, dy[4] = {-1, 0, 1, 0};
 #pragma unroll
@@ -134,7 +134,7 @@ __device__ __forceinline__ void gather_cell(const GridView& g, const T* __restri
     bool b = (nx < 0) | (nx >= g.X) | (ny < 0) | (ny >= g.Y) | c.term;
     if (!b) b = bit(g.wall, dy[a], nx);
     if (!b) {
-      c.vn[a] = vin[base + static_cast<ptrdiff_t>(dy[a]) * g.pitch + dx[a]];
+      c.vn[a] = vin != nullptr ? vin[base + static_cast<ptrdiff_t>(dy[a]) * g.pitch + dx[a]] : T(0);
       c.rn[a] = reward_of(bit(g.goal, dy[a], nx), bit(g.lava, dy[a], nx));
     } else {
       c.vn[a] = c.vs;

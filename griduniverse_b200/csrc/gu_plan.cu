@@ -105,8 +105,18 @@ int greedy_tiled_f32(const gu_grid*, const float*, uint8_t*, float, cudaStream_t
 int greedy_tiled_f64(const gu_grid*, const double*, uint8_t*, double, cudaStream_t);
 
 // ---- whole VI loop in one thread block (grids that fit in shared memory) ---------------
-constexpr int kSmallThreads = 1024;
 constexpr int64_t kSmallMaxCells = 13000;   // 2 x f64 + 1 info byte per cell within 227 KB
+
+// A batch of same-shape mazes, one thread block each (blockIdx.x = maze): maze m's planes start
+// plane_stride words, its per-cell arrays cell_stride elements after maze m-1's (0 for a single grid).
+struct BatchStrides {
+  long long plane, cell;
+};
+__device__ __forceinline__ GridView maze_view(GridView g, const BatchStrides& b) {
+  const long long o = static_cast<long long>(blockIdx.x) * b.plane;
+  g.wall += o; g.goal += o; g.lava += o;
+  return g;
+}
 
 // info byte: bits 0-3 = blocked per action, bit 4 = goal, bit 5 = lava
 __device__ __forceinline__ void small_cell(const double* va, const uint8_t* info, int s, int X,
@@ -131,11 +141,23 @@ __device__ __forceinline__ void small_cell(const double* va, const uint8_t* info
   }
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 1)
-vi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ vout,
+template <int kSmallThreads>
+__global__ void __launch_bounds__(kSmallThreads)
+vi_small_kernel(GridView g0, BatchStrides bs, const double* __restrict__ v0, double* __restrict__ vout,
                 uint8_t* __restrict__ tie, int kind0, const void* __restrict__ policy, double gamma,
                 double threshold, int max_steps, int32_t* sweeps_out, double* last_delta) {
   extern __shared__ double smem_d[];
+  const GridView g = maze_view(g0, bs);
+  {                                             // this maze's slice of every per-cell array
+    const long long o = static_cast<long long>(blockIdx.x) * bs.cell;
+    if (v0 != nullptr) v0 += o;
+    vout += o;
+    tie += o;
+    if (policy != nullptr)
+      policy = static_cast<const char*>(policy) + o * (kind0 == GU_POLICY_PROBS ? 4 * sizeof(double) : 1);
+    sweeps_out += blockIdx.x;
+    last_delta += blockIdx.x;
+  }
   const int N = g.X * g.Y;
   double* va = smem_d;
   double* vb = smem_d + N;
@@ -177,7 +199,7 @@ vi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ 
     if ((tid & 31) == 0) red[tid >> 5] = dmax;
     __syncthreads();
     if (tid < 32) {
-      double w = warp_max(red[tid]);
+      double w = warp_max(tid < kSmallThreads / 32 ? red[tid] : -CUDART_INF);
       if (tid == 0) delta_sh = w;
     }
     __syncthreads();
@@ -214,18 +236,30 @@ __device__ __forceinline__ double block_max(double v, double* red, double* out) 
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
   __syncthreads();
   if (threadIdx.x < 32) {
-    const double w = warp_max(red[threadIdx.x]);
+    const double w = warp_max(threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : -CUDART_INF);
     if (threadIdx.x == 0) *out = w;
   }
   __syncthreads();
   return *out;
 }
 
-__global__ void __launch_bounds__(kSmallThreads, 1)
-pi_small_kernel(GridView g, const double* __restrict__ v0, double* __restrict__ vout,
+template <int kSmallThreads>
+__global__ void __launch_bounds__(kSmallThreads)
+pi_small_kernel(GridView g0, BatchStrides bs, const double* __restrict__ v0, double* __restrict__ vout,
                 uint8_t* __restrict__ tie, int kind0, const void* __restrict__ policy, double gamma,
                 double threshold, int max_steps, int32_t* meta, double* last_delta_eval) {
   extern __shared__ double smem_d[];
+  const GridView g = maze_view(g0, bs);
+  {
+    const long long o = static_cast<long long>(blockIdx.x) * bs.cell;
+    if (v0 != nullptr) v0 += o;
+    vout += o;
+    tie += o;
+    if (policy != nullptr)
+      policy = static_cast<const char*>(policy) + o * (kind0 == GU_POLICY_PROBS ? 4 * sizeof(double) : 1);
+    meta += 3 * blockIdx.x;
+    last_delta_eval += blockIdx.x;
+  }
   const int N = g.X * g.Y;
   double* v = smem_d;               // current value function
   double* scratch = smem_d + N;
@@ -367,6 +401,61 @@ extern "C" __attribute__((visibility("default"))) int gu_greedy_f32(const gu_gri
   return greedy_generic<float>(g, v, tie_mask, gamma, static_cast<cudaStream_t>(stream));
 }
 
+namespace gu {
+// Block size for a maze of N cells: enough threads for one cell each up to 1024, so that small mazes
+// leave room for many resident blocks (= mazes in flight) per SM.
+template <bool PI, int THREADS>
+static int launch_small_t(const GridView& v, BatchStrides bs, int n_mazes, size_t smem, const double* v0,
+                          double* v_out, uint8_t* tie, int kind, const void* policy, double gamma, double threshold,
+                          int max_steps, int32_t* meta, double* delta, cudaStream_t st) {
+  if (PI) {
+    cudaError_t e = cudaFuncSetAttribute(pi_small_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    pi_small_kernel<THREADS><<<n_mazes, THREADS, smem, st>>>(v, bs, v0, v_out, tie, kind, policy, gamma, threshold,
+                                                             max_steps, meta, delta);
+  } else {
+    cudaError_t e = cudaFuncSetAttribute(vi_small_kernel<THREADS>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    vi_small_kernel<THREADS><<<n_mazes, THREADS, smem, st>>>(v, bs, v0, v_out, tie, kind, policy, gamma, threshold,
+                                                             max_steps, meta, delta);
+  }
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+template <bool PI>
+static int launch_small(const GridView& v, BatchStrides bs, int n_mazes, bool single, const double* v0, double* v_out,
+                        uint8_t* tie, int kind, const void* policy, double gamma, double threshold, int max_steps,
+                        int32_t* meta, double* delta, cudaStream_t st) {
+  const int64_t N = static_cast<int64_t>(v.X) * v.Y;
+  const size_t smem = static_cast<size_t>(N) * (PI ? 26 : 17) + 16;
+#define GU_SMALL(T) launch_small_t<PI, T>(v, bs, n_mazes, smem, v0, v_out, tie, kind, policy, gamma, threshold, max_steps, meta, delta, st)
+  if (single || N > 2048) return GU_SMALL(1024);     // one grid: the whole SM works on it
+  if (N > 512) return GU_SMALL(512);
+  if (N > 128) return GU_SMALL(256);
+  return GU_SMALL(128);
+#undef GU_SMALL
+}
+
+static int check_batch(const gu_grid_batch* b, int64_t max_cells) {
+  if (!b || !b->wall || !b->goal || !b->lava) return GU_ERR_NULL;
+  const int64_t N = static_cast<int64_t>(b->X) * b->Y;
+  if (b->X <= 0 || b->Y <= 0 || N > max_cells || b->n_mazes < 0 || b->pitch < b->X || b->pitch_words * 32 < b->X ||
+      b->cell_stride < static_cast<int64_t>(b->Y + 2) * b->pitch ||
+      b->plane_stride < static_cast<int64_t>(b->Y + 2) * b->pitch_words)
+    return GU_ERR_SHAPE;
+  return GU_OK;
+}
+static GridView batch_view(const gu_grid_batch* b) {
+  GridView v;
+  v.X = b->X; v.Y = b->Y; v.row_begin = 0; v.row_end = b->Y; v.pitch = b->pitch; v.pitch_words = b->pitch_words;
+  v.wall = b->wall; v.goal = b->goal; v.lava = b->lava;
+  return v;
+}
+}  // namespace gu
+
 extern "C" __attribute__((visibility("default"))) int64_t gu_vi_small_max_cells(void) { return kSmallMaxCells; }
 
 extern "C" __attribute__((visibility("default"))) int gu_vi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* tie_mask,
@@ -379,15 +468,23 @@ extern "C" __attribute__((visibility("default"))) int gu_vi_small_f64(const gu_g
   if (policy_kind < 0 || policy_kind > GU_POLICY_GREEDY) return GU_ERR_MODE;
   const int64_t N = static_cast<int64_t>(g->X) * g->Y;
   if (g->row_begin != 0 || g->row_end != g->Y || N > kSmallMaxCells || max_steps < 0) return GU_ERR_SHAPE;
-  const size_t smem = static_cast<size_t>(N) * 17 + 16;
-  cudaError_t e = cudaFuncSetAttribute(vi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
-  vi_small_kernel<<<1, kSmallThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      view_of(g), v0, v_out, tie_mask, policy_kind, policy, gamma, threshold, max_steps, sweeps_out,
-      last_delta);
-  GU_CHECK_LAUNCH();
-  return GU_OK;
+  return launch_small<false>(view_of(g), BatchStrides{0, 0}, 1, true, v0, v_out, tie_mask, policy_kind, policy, gamma,
+                             threshold, max_steps, sweeps_out, last_delta, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_vi_batch_f64(
+    const gu_grid_batch* b, const double* v0, double* v_out, uint8_t* tie_mask, int policy_kind, const void* policy,
+    double gamma, double threshold, int32_t max_steps, int32_t* sweeps_out, double* last_delta, void* stream) {
+  int rc = check_batch(b, kSmallMaxCells);
+  if (rc) return rc;
+  if (!v_out || !tie_mask || !sweeps_out || !last_delta) return GU_ERR_NULL;
+  if (policy_kind < GU_POLICY_PROBS || policy_kind > GU_POLICY_GREEDY) return GU_ERR_MODE;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  if (max_steps < 0) return GU_ERR_SHAPE;
+  if (b->n_mazes == 0) return GU_OK;
+  return launch_small<false>(batch_view(b), BatchStrides{b->plane_stride, b->cell_stride}, b->n_mazes, false, v0, v_out,
+                             tie_mask, policy_kind, policy, gamma, threshold, max_steps, sweeps_out, last_delta,
+                             static_cast<cudaStream_t>(stream));
 }
 
 extern "C" __attribute__((visibility("default"))) int64_t gu_pi_small_max_cells(void) { return kPiSmallMaxCells; }
@@ -400,12 +497,21 @@ extern "C" __attribute__((visibility("default"))) int gu_pi_small_f64(
   if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
   const int64_t N = static_cast<int64_t>(g->X) * g->Y;
   if (g->row_begin != 0 || g->row_end != g->Y || N > kPiSmallMaxCells || max_steps < 0) return GU_ERR_SHAPE;
-  const size_t smem = static_cast<size_t>(N) * 26 + 16;
-  cudaError_t e = cudaFuncSetAttribute(pi_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       static_cast<int>(smem));
-  if (e != cudaSuccess) return static_cast<int>(e);
-  pi_small_kernel<<<1, kSmallThreads, smem, static_cast<cudaStream_t>(stream)>>>(
-      view_of(g), v0, v_out, tie_mask, policy_kind, policy, gamma, threshold, max_steps, meta, last_delta_eval);
-  GU_CHECK_LAUNCH();
-  return GU_OK;
+  return launch_small<true>(view_of(g), BatchStrides{0, 0}, 1, true, v0, v_out, tie_mask, policy_kind, policy, gamma,
+                            threshold, max_steps, meta, last_delta_eval, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_pi_batch_f64(
+    const gu_grid_batch* b, const double* v0, double* v_out, uint8_t* tie_mask, int policy_kind, const void* policy,
+    double gamma, double threshold, int32_t max_steps, int32_t* meta, double* last_delta_eval, void* stream) {
+  int rc = check_batch(b, kPiSmallMaxCells);
+  if (rc) return rc;
+  if (!v_out || !tie_mask || !meta || !last_delta_eval) return GU_ERR_NULL;
+  if (policy_kind < GU_POLICY_PROBS || policy_kind > GU_POLICY_GREEDY) return GU_ERR_MODE;
+  if ((policy_kind == GU_POLICY_PROBS || policy_kind == GU_POLICY_MASK) && !policy) return GU_ERR_NULL;
+  if (max_steps < 0) return GU_ERR_SHAPE;
+  if (b->n_mazes == 0) return GU_OK;
+  return launch_small<true>(batch_view(b), BatchStrides{b->plane_stride, b->cell_stride}, b->n_mazes, false, v0, v_out,
+                            tie_mask, policy_kind, policy, gamma, threshold, max_steps, meta, last_delta_eval,
+                            static_cast<cudaStream_t>(stream));
 }

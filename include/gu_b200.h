@@ -330,6 +330,31 @@ int gu_pi_small_f64(const gu_grid* g, const double* v0, double* v_out, uint8_t* 
                     int32_t max_steps, int32_t* meta, double* last_delta_eval, void* stream);
 int64_t gu_pi_small_max_cells(void);
 
+/* A batch of n_mazes same-shape grids solved in ONE launch, one thread block per maze (the many
+ * small mazes of the reference's examples, examples/griduniverse_alg_examples.py:29-59; independent
+ * units: shard them over GPUs by maze range, no collective).  Maze m's bit planes start
+ * m * plane_stride uint32 words and its per-cell arrays (v0, v_out, tie_mask, policy) m * cell_stride
+ * elements after maze 0's, each laid out like a whole grid in struct gu_grid: Y + 2 rows of pitch / pitch_words.
+ * Per-maze outputs: sweeps_out / last_delta (value iteration), meta[m][3] = {sweeps, improved,
+ * exhausted} / last_delta_eval (policy iteration) -- same meaning as gu_vi_small_f64 / gu_pi_small_f64,
+ * to which every maze's result is bit-identical.  v0 = NULL: value functions of zeros. */
+typedef struct {
+  int32_t X, Y;
+  int32_t n_mazes;
+  int32_t pitch, pitch_words;
+  int64_t cell_stride;
+  int64_t plane_stride;
+  const uint32_t* wall;
+  const uint32_t* goal;
+  const uint32_t* lava;
+} gu_grid_batch;
+int gu_vi_batch_f64(const gu_grid_batch* b, const double* v0, double* v_out, uint8_t* tie_mask, int policy_kind,
+                    const void* policy, double gamma, double threshold, int32_t max_steps, int32_t* sweeps_out,
+                    double* last_delta, void* stream);
+int gu_pi_batch_f64(const gu_grid_batch* b, const double* v0, double* v_out, uint8_t* tie_mask, int policy_kind,
+                    const void* policy, double gamma, double threshold, int32_t max_steps, int32_t* meta,
+                    double* last_delta_eval, void* stream);
+
 /* ---- synthetic levels (not in the reference; pure functions of seed and index) -------- */
 
 /* Per-env levels for envs [first_env, first_env + n_envs): border open, 20 % interior walls,

@@ -22,7 +22,18 @@ import types
 
 import numpy as np
 
-REFERENCE_ROOT = os.environ.get("GU_REFERENCE_ROOT", "/root/reference")
+def _find_reference():
+    """GU_REFERENCE_ROOT, else /root/reference (authoring container), else baseline/_ref (a copy the
+    driver may place next to the repo); the first that holds core/envs."""
+    here = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cands = [os.environ.get("GU_REFERENCE_ROOT"), "/root/reference", os.path.join(here, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "core", "envs")):
+            return c
+    return cands[0] or "/root/reference"
+
+
+REFERENCE_ROOT = _find_reference()
 
 
 def reference_available():

@@ -1,0 +1,92 @@
+"""TEST / BENCH INFRASTRUCTURE ONLY -- CPU timing of the UNMODIFIED reference (through ref_shim).
+
+bench.py's ``cpu_baseline`` leg calls this when the reference tree is present (the authoring
+container: /root/reference; a box where the driver put it under baseline/_ref).  It is absent on the
+GPU box (a Python reference cannot travel), where only the oracle port is timed; the numbers measured
+here are committed under profiles/ (SURVEY section 8d items i, iii, iv)."""
+import json
+import os
+import time
+import warnings
+
+import numpy as np
+
+from . import ref_shim
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def available():
+    return ref_shim.reference_available()
+
+
+def time_reference(cfg2_level_lines=None):
+    """Returns a dict of the reference's own timings on ONE core (its loops are single-threaded)."""
+    ref = ref_shim.load()
+    Env = ref.GridUniverseEnv
+    out = {"kind": "reference", "cores": 1, "root": ref_shim.REFERENCE_ROOT}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        # B1 / cfg 1: default 4x4 env, 1000 host-supplied random steps, reset on done
+        env = Env()
+        acts = np.random.RandomState(0).randint(0, 4, 1000)
+        env.reset()
+        reps = 10
+        t = time.perf_counter()
+        for _ in range(reps):
+            for a in acts:
+                _, _, done, _ = env.step(int(a))
+                if done:
+                    env.reset()
+        dt = time.perf_counter() - t
+        out["cfg1"] = {"us_per_step": dt / (reps * 1000) * 1e6, "steps_per_s": reps * 1000 / dt,
+                       "sample": "%d x 1000 steps of GridUniverseEnv().step (griduniverse_env.py:176-185)" % reps}
+        # B3 / cfg 2: 10x10 generated maze, gamma 0.9, theta 1e-6
+        if cfg2_level_lines is None:
+            with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:
+                cfg2_level_lines = json.load(f)["gen10_0"]
+        import tempfile
+        with tempfile.NamedTemporaryFile("w", suffix=".txt", delete=False) as f:
+            f.write("\n".join(cfg2_level_lines) + "\n")
+            fp = f.name
+        env = Env(custom_world_fp=fp)
+        os.unlink(fp)
+        N = env.world.size
+        cfg2 = {}
+        for name, fn in (("value_iteration", ref.dp.value_iteration), ("policy_iteration", ref.dp.policy_iteration)):
+            calls = {"n": 0}
+            orig = ref.utils.single_step_policy_evaluation
+
+            def counted(*a, **k):
+                calls["n"] += 1
+                return orig(*a, **k)
+
+            ref.utils.single_step_policy_evaluation = counted
+            try:
+                t = time.perf_counter()
+                fn(np.ones([N, 4]) / 4, env, np.zeros(N), threshold=1e-6, max_steps=1000, discount_factor=0.9)
+                dt = time.perf_counter() - t
+            finally:
+                ref.utils.single_step_policy_evaluation = orig
+            cfg2[name] = {"ms_per_solve": dt * 1e3, "sweeps": calls["n"], "cell_updates_per_s": calls["n"] * N / dt}
+        cfg2["sample"] = "one 10x10 reference-generated maze (tests/golden/levels.json gen10_0), one solve each"
+        out["cfg2"] = cfg2
+        # B4: one sweep + one greedy extraction on the largest shipped level
+        fp = os.path.join(ref_shim.REFERENCE_ROOT, "core", "envs", "maze_text_files", "maze_101x101.txt")
+        if os.path.exists(fp):
+            env = Env(custom_world_fp=fp)
+            N = env.world.size
+            P = np.ones([N, 4]) / 4
+            t0 = time.perf_counter()
+            v = ref.utils.single_step_policy_evaluation(P, env, 0.9, np.zeros(N))
+            t1 = time.perf_counter()
+            ref.utils.greedy_policy_from_value_function(P, env, v, 0.9)
+            t2 = time.perf_counter()
+            out["maze_101x101"] = {"sweep_us_per_cell": (t1 - t0) / N * 1e6, "greedy_us_per_cell": (t2 - t1) / N * 1e6,
+                                   "cell_updates_per_s": N / (t2 - t0),
+                                   "sample": "one single_step_policy_evaluation + one greedy_policy_from_value_function"}
+    return out
+
+
+if __name__ == "__main__":
+    print(json.dumps(time_reference(), indent=1))
