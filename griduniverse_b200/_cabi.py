@@ -15,11 +15,12 @@ c_ptr = ctypes.c_void_p
 GU_FLAG_AUTO_RESET = 1
 GU_FLAG_NO_CARE_TERMINAL = 2
 GU_FLAG_ACCUMULATE = 4
+GU_FLAG_PACKED_ACTIONS = 8
 GU_BFS_LAVA_BLOCKS = 1
 GU_TEXT_NO_START, GU_TEXT_NO_GOAL = -1, -2
 GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
 
-EXPORTS = ("gu_step", "gu_rollout", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
+EXPORTS = ("gu_step", "gu_rollout", "gu_pack_actions", "gu_pack_actions_host", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_evaluate_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
            "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_max_diff_f32", "gu_max_diff_f64", "gu_vi_small_f64",
            "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_vi_batch_f64", "gu_pi_batch_f64", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_version", "gu_arch", "gu_error_string")
 
@@ -90,9 +91,13 @@ def lib():
     sig = {
         "gu_step": (ctypes.c_int, [lvp, i64, p, p, p, p, p, p, p, u32, p]),
         "gu_rollout": (ctypes.c_int, [lvp, i64, i64, p, p, p, p, p, p, p, p, p, p, u32, p]),
+        "gu_pack_actions": (ctypes.c_int, [p, i64, i64, p, p]),
+        "gu_pack_actions_host": (ctypes.c_int, [p, i64, i64, p, i32]),
         "gu_rollout_policy": (ctypes.c_int, [lvp, i64, i64, p, p, p, p, p, p, p, p]),
         "gu_mc_episode_f64": (ctypes.c_int, [i32, i32, p, p, p, i64, p, p, i32, i32, f64, p, p, p, p, p]),
         "gu_mc_finalize_f64": (ctypes.c_int, [i32, p, p, p, p]),
+        "gu_mc_evaluate_f64": (ctypes.c_int, [lvp, p, p, i64, p, i32, i32, p, p, i32, i32, f64, p, p, p, p, p, p, p, p,
+                                              p, p]),
         "gu_synth_env_levels": (ctypes.c_int, [i32, i32, i64, i64, u32, p, p, p, p, p]),
         "gu_synth_maze": (ctypes.c_int, [i32, i32, i32, i32, i32, u32, p, p, p, p]),
         "gu_tables_bytes": (i64, [lvp, i64]),
@@ -134,6 +139,24 @@ def lib():
 def check(fn_name, code):
     if code != 0:
         raise GuError(fn_name, code, lib().gu_error_string(code).decode())
+
+
+def on_device(fn):
+    """Method decorator: run with ``self.device`` as the current CUDA device.  Every C-ABI call enqueues
+    on the CURRENT stream of the CURRENT device, so an object living on cuda:1 must make cuda:1
+    current for the duration of the call (otherwise its kernels would be launched on another GPU's
+    stream with this GPU's pointers)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        import torch
+        dev = getattr(self, "device", None)
+        if dev is None or dev.index is None or dev.index == torch.cuda.current_device():
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(self, *args, **kwargs)
+    return wrapper
 
 
 def ptr(t):

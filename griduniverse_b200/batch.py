@@ -92,6 +92,7 @@ class MazeBatch(object):
         return _cabi.GU_POLICY_PROBS, self.pad(pol.astype(np.float64), torch.float64)
 
     # ---- solvers --------------------------------------------------------------------------------
+    @_cabi.on_device
     def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
                         discount_factor=1.0):
         """dynamic_programming.py:8-28 for every maze.  Returns (V [n, N] f64, tie masks [n, N] u8,
@@ -108,6 +109,7 @@ class MazeBatch(object):
         self.launches += 1
         return self.dense(v), self.dense(tie), sweeps, delta
 
+    @_cabi.on_device
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
                          discount_factor=1.0):
         """dynamic_programming.py:31-57 for every maze.  Returns (V_lastconv [n, N], tie masks [n, N],

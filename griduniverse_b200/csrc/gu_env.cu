@@ -124,12 +124,21 @@ rollout_generic_kernel(LevelsView lv, int64_t T, const int32_t* __restrict__ act
   long long rsum = 0, dcnt = 0;
   if (i < lv.N) {
     int s = pos[i];
-    const int st = start_of(lv, i);
+    const int st = auto_reset && !start_choice ? start_of(lv, i) : 0;    // lv.start may be NULL otherwise
+    const bool packed = flags & GU_FLAG_PACKED_ACTIONS;
+    uint32_t word = 0;
     for (int64_t t = 0; t < T; ++t) {
       const int64_t o = t * lv.N + i;
       int n, r;
       bool d;
-      transition(lv, i, s, __ldg(actions + o), care, n, r, d);
+      int a;
+      if (packed) {                                   // 16 steps per word: uint32[ceil(T/16)][N]
+        if ((t & 15) == 0) word = static_cast<uint32_t>(__ldg(actions + (t >> 4) * lv.N + i));
+        a = static_cast<int>((word >> (2 * (t & 15))) & 3u);
+      } else {
+        a = __ldg(actions + o);
+      }
+      transition(lv, i, s, a, care, n, r, d);
       if (obs) obs[o] = n;
       if (reward) reward[o] = r;
       if (done) done[o] = d;
@@ -175,6 +184,12 @@ rollout_policy_kernel(LevelsView lv, int64_t T, const double* __restrict__ cdf,
     const int64_t o = t * lv.N + i;
     const double u = __ldg(uniforms + o);
     const double* row = cdf + static_cast<int64_t>(s) * 4;
+    if (__ldg(row + 3) != __ldg(row + 3)) {          // NaN row: np.random.choice would raise in this state
+      pos[i] = s;
+      if (length) length[i] = static_cast<int32_t>(-1 - t);
+      if (done) done[i] = 0;
+      return;
+    }
     // searchsorted(cdf, u, side='right'): number of entries <= u (cdf[3] == 1 > u)
     int a = (__ldg(row) <= u) + (__ldg(row + 1) <= u) + (__ldg(row + 2) <= u);
     int n, r;
@@ -197,9 +212,75 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
                    int32_t* env_return, int32_t* env_done, int64_t* stats, const uint32_t* tables,
                    uint32_t flags, cudaStream_t st);
 
+// int32 actions [T][N] -> packed 2-bit actions uint32[ceil(T/16)][N] (GU_FLAG_PACKED_ACTIONS)
+__global__ void __launch_bounds__(256)
+pack_actions_kernel(const int32_t* __restrict__ actions, uint32_t* __restrict__ packed, int64_t T, int64_t N) {
+  const int64_t i = static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const int64_t w = blockIdx.y;
+  if (i >= N) return;
+  uint32_t word = 0;
+#pragma unroll
+  for (int s = 0; s < 16; ++s) {
+    const int64_t t = w * 16 + s;
+    if (t < T) word |= (static_cast<uint32_t>(__ldg(actions + t * N + i)) & 3u) << (2 * s);
+  }
+  packed[w * N + i] = word;
+}
+
+}  // namespace gu
+
+#include <thread>
+#include <vector>
+
+namespace gu {
+static void pack_rows_host(const int32_t* actions, uint32_t* packed, int64_t T, int64_t N, int64_t w0, int64_t w1) {
+  for (int64_t w = w0; w < w1; ++w) {
+    uint32_t* out = packed + w * N;
+    const int steps = static_cast<int>(T - w * 16 < 16 ? T - w * 16 : 16);
+    for (int64_t i = 0; i < N; ++i) out[i] = static_cast<uint32_t>(actions[w * 16 * N + i]) & 3u;
+    for (int s = 1; s < steps; ++s) {
+      const int32_t* row = actions + (w * 16 + s) * N;
+      for (int64_t i = 0; i < N; ++i) out[i] |= (static_cast<uint32_t>(row[i]) & 3u) << (2 * s);
+    }
+  }
+}
 }  // namespace gu
 
 using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_pack_actions(const int32_t* actions, int64_t n_steps,
+                                                                        int64_t n_envs, uint32_t* packed, void* stream) {
+  if (n_steps < 0 || n_envs < 0) return GU_ERR_SHAPE;
+  if (n_steps == 0 || n_envs == 0) return GU_OK;
+  if (!actions || !packed) return GU_ERR_NULL;
+  const int64_t words = (n_steps + 15) / 16;
+  if (words > 65535) return GU_ERR_SHAPE;
+  dim3 grid(static_cast<unsigned>((n_envs + 255) / 256), static_cast<unsigned>(words));
+  pack_actions_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(actions, packed, n_steps, n_envs);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_pack_actions_host(const int32_t* actions, int64_t n_steps,
+                                                                             int64_t n_envs, uint32_t* packed,
+                                                                             int32_t n_threads) {
+  if (n_steps < 0 || n_envs < 0) return GU_ERR_SHAPE;
+  if (n_steps == 0 || n_envs == 0) return GU_OK;
+  if (!actions || !packed) return GU_ERR_NULL;
+  const int64_t words = (n_steps + 15) / 16;
+  int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
+  if (nt < 1) nt = 1;
+  if (nt > words) nt = static_cast<int>(words);
+  if (nt == 1) {
+    pack_rows_host(actions, packed, n_steps, n_envs, 0, words);
+    return GU_OK;
+  }
+  std::vector<std::thread> pool;
+  for (int k = 0; k < nt; ++k)
+    pool.emplace_back(pack_rows_host, actions, packed, n_steps, n_envs, words * k / nt, words * (k + 1) / nt);
+  for (auto& t : pool) t.join();
+  return GU_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* lv, int64_t n, const int32_t* actions, int32_t* pos, int32_t* obs,
                        int32_t* reward, uint8_t* done, const int32_t* start_choice, int64_t* stats,

@@ -75,7 +75,6 @@ pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
 #ifndef GU_ROLLOUT_WARPS
 #define GU_ROLLOUT_WARPS 4
 #endif
-constexpr int kBulkWarps = GU_ROLLOUT_WARPS;    // warps per block of the TMA rollout kernel (each warp is independent)
 
 // ---- rollout over INFO8 tables, TMA-tiled staging ---------------------------------------------------
 // A warp owns 32*EPT consecutive envs and lane l steps envs l, l+32, ...  All HBM traffic is 2-D
@@ -95,8 +94,13 @@ constexpr int kBulkWarps = GU_ROLLOUT_WARPS;    // warps per block of the TMA ro
 #ifndef GU_INFO8_STAGES
 #define GU_INFO8_STAGES 2
 #endif
-constexpr int kInfoRows = GU_INFO8_ROWS;       // action rows (time steps) per TMA box
-constexpr int kInfoStages = GU_INFO8_STAGES;
+// Ring geometry (template parameters of the kernel): action rows per TMA box, boxes in flight per
+// warp, warps per block.  Large batches use the shallow ring (more resident warps per SM); batches that
+// leave every SM with only a dozen warps use a deep one -- 4 x 16 rows = 8 KB in flight per warp --
+// because then the bytes in flight, not the warp count, bound the achieved bandwidth (BASELINE cfg 3:
+// 65,536 envs = 14 warps per SM, 0.46 of the HBM roofline with the shallow ring).
+struct RingStd { static constexpr int kRows = GU_INFO8_ROWS, kStages = GU_INFO8_STAGES, kWarps = GU_ROLLOUT_WARPS; };
+struct RingDeep { static constexpr int kRows = 16, kStages = 4, kWarps = 2; };
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
@@ -108,14 +112,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
                ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
 }
 
-template <int EPT, bool TRAJ, bool AUTO_RESET>
-__global__ void __launch_bounds__(kBulkWarps * 32)
+// PACKED: the action stream holds 2 bits per step, 16 steps per 32-bit word (uint32[ceil(T/16)][N],
+// step t of env n in bits 2*(t % 16) of word [t / 16][n]): a sixteenth of the bytes, the same steps.
+template <int EPT, bool TRAJ, bool AUTO_RESET, typename RING, bool PACKED>
+__global__ void __launch_bounds__(RING::kWarps * 32)
 rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap tab_map,
                          int N, int T, int X, int words, int32_t* __restrict__ pos, int32_t* __restrict__ obs,
                          int32_t* __restrict__ reward, uint8_t* __restrict__ done,
                          const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
                          int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  constexpr int kInfoRows = RING::kRows, kInfoStages = RING::kStages, kBulkWarps = RING::kWarps;
   constexpr int EPW = 32 * EPT, ROWB = EPW * 4;
   constexpr uint32_t kBoxBytes = kInfoRows * ROWB;
   const int lane = threadIdx.x & 31;
@@ -128,7 +135,8 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
   const uint32_t bar_tab = bar0 + 8 * kInfoStages;
   const int env0 = (blockIdx.x * kBulkWarps + warp) * EPW;               // N % EPW == 0
   const bool accumulate = flags & GU_FLAG_ACCUMULATE;
-  const int nbatch = (T + kInfoRows - 1) / kInfoRows;
+  const int Trows = PACKED ? (T + 15) / 16 : T;                       // rows of the action matrix
+  const int nbatch = (Trows + kInfoRows - 1) / kInfoRows;
   // signed byte LUT of the four moves: UP -X, RIGHT +1, DOWN +X, LEFT -1
   const uint32_t deltas = (static_cast<uint32_t>(-X) & 0xffu) | (1u << 8) | ((static_cast<uint32_t>(X) & 0xffu) << 16) |
                           (0xffu << 24);
@@ -155,7 +163,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       p[k] = pos[env0 + k * 32 + lane];
-      st[k] = start[env0 + k * 32 + lane];
+      st[k] = AUTO_RESET ? start[env0 + k * 32 + lane] : 0;      // lv->start may be NULL without auto-reset
       fsum[k] = 0;
       fsq[k] = 0;
       tabk[k] = tab_s + (k * 32 + lane) * 4;
@@ -170,31 +178,50 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       inf[k] = info_at(k, p[k]);
-      inf_st[k] = info_at(k, st[k]);
+      inf_st[k] = AUTO_RESET ? info_at(k, st[k]) : 0u;
     }
 
-    auto step_row = [&](uint32_t arow, int t) {      // arow: smem address of this lane's word in the action row
+    auto step_one = [&](int k, uint32_t a, int t) {
+      const uint32_t allowed = (inf[k] >> a) & 1u;
+      // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
+      int d, n;
+      asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
+      asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
+      uint32_t i2 = info_at(k, n);
+      const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
+      if (TRAJ) {
+        const int64_t o = static_cast<int64_t>(t) * N + env0 + k * 32 + lane;
+        if (obs) obs[o] = n;
+        if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
+        if (done) done[o] = f ? 1 : 0;
+      }
+      fsum[k] += f;                               // 64*goals + 128*lavas
+      fsq[k] += f * f;                            // 4096*goals + 16384*lavas
+      if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
+      p[k] = n;
+      inf[k] = i2;
+    };
+    // one row of the action matrix: one step (int32 actions) or sixteen (packed)
+    auto step_row = [&](uint32_t arow, int row, bool full) {   // arow: smem address of this lane's word in the row
+      if (!PACKED) {
 #pragma unroll
-      for (int k = 0; k < EPT; ++k) {
-        const uint32_t a = lds_u32(arow + k * 128) & 3u;
-        const uint32_t allowed = (inf[k] >> a) & 1u;
-        // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
-        int d, n;
-        asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
-        asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
-        uint32_t i2 = info_at(k, n);
-        const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
-        if (TRAJ) {
-          const int64_t o = static_cast<int64_t>(t) * N + env0 + k * 32 + lane;
-          if (obs) obs[o] = n;
-          if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
-          if (done) done[o] = f ? 1 : 0;
+        for (int k = 0; k < EPT; ++k) step_one(k, lds_u32(arow + k * 128) & 3u, row);
+      } else {
+        uint32_t w[EPT];
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) w[k] = lds_u32(arow + k * 128);
+        if (full) {
+#pragma unroll
+          for (int s = 0; s < 16; ++s) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s);
+          }
+        } else {
+          for (int s = 0; row * 16 + s < T; ++s) {
+#pragma unroll
+            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s);
+          }
         }
-        fsum[k] += f;                               // 64*goals + 128*lavas
-        fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-        if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
-        p[k] = n;
-        inf[k] = i2;
       }
     };
 
@@ -204,11 +231,11 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
       const int t0 = b * kInfoRows;
       mbar_wait(bar0 + 8 * stage, parity);
       const uint32_t arow = act_s + stage * kBoxBytes + lane * 4;
-      if (t0 + kInfoRows <= T) {
-#pragma unroll
-        for (int r = 0; r < kInfoRows; ++r) step_row(arow + r * ROWB, t0 + r);
-      } else {
-        for (int r = 0; t0 + r < T; ++r) step_row(arow + r * ROWB, t0 + r);   // rows past T are zero fill
+      if (PACKED ? (t0 + kInfoRows) * 16 <= T : t0 + kInfoRows <= T) {
+#pragma unroll (PACKED ? 1 : kInfoRows)
+        for (int r = 0; r < kInfoRows; ++r) step_row(arow + r * ROWB, t0 + r, true);
+      } else {                                         // rows past the end are zero fill and never stepped
+        for (int r = 0; t0 + r < Trows; ++r) step_row(arow + r * ROWB, t0 + r, !PACKED || (t0 + r + 1) * 16 <= T);
       }
       __syncwarp();                                   // every lane is done with this stage
       if (b + kInfoStages < nbatch && elect_one()) {
@@ -262,23 +289,30 @@ static bool make_map_i32(CUtensorMap* map, const void* base, int64_t rows, int64
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int EPT, bool TRAJ, bool AR>
+template <typename RING>
+static size_t info8_smem_bytes(int words, int ept) {
+  return static_cast<size_t>(RING::kWarps) * (static_cast<size_t>(words) + RING::kStages * RING::kRows) * 32 * ept * 4 + 128;
+}
+
+template <int EPT, bool TRAJ, bool AR, typename RING, bool PACKED>
 static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
                         int32_t* reward, uint8_t* done, int32_t* env_return, int32_t* env_done, int64_t* stats,
                         const uint32_t* tables, uint32_t flags, cudaStream_t st) {
   const int cells = lv->X * lv->Y, words = (cells + 3) / 4;
   constexpr int EPW = 32 * EPT;
+  const int64_t act_rows = PACKED ? (T + 15) / 16 : T;
   CUtensorMap act_map, tab_map;
-  if (!make_map_i32(&act_map, actions, T, n, kInfoRows, EPW) || !make_map_i32(&tab_map, tables, words, n, words, EPW))
+  if (!make_map_i32(&act_map, actions, act_rows, n, RING::kRows, EPW) ||
+      !make_map_i32(&tab_map, tables, words, n, words, EPW))
     return GU_ERR_UNSUPPORTED;
-  const size_t smem = static_cast<size_t>(kBulkWarps) * (static_cast<size_t>(words) + kInfoStages * kInfoRows) * EPW * 4 + 128;
-  const unsigned blocks = static_cast<unsigned>((n / EPW + kBulkWarps - 1) / kBulkWarps);
-  cudaError_t e = cudaFuncSetAttribute(rollout_info8_tma_kernel<EPT, TRAJ, AR>,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  const size_t smem = info8_smem_bytes<RING>(words, EPT);
+  const unsigned blocks = static_cast<unsigned>((n / EPW + RING::kWarps - 1) / RING::kWarps);
+  auto kernel = rollout_info8_tma_kernel<EPT, TRAJ, AR, RING, PACKED>;
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  rollout_info8_tma_kernel<EPT, TRAJ, AR><<<blocks, kBulkWarps * 32, smem, st>>>(
-      act_map, tab_map, static_cast<int>(n), static_cast<int>(T), lv->X, words, pos, obs, reward, done, lv->start,
-      env_return, env_done, stats, flags);
+  kernel<<<blocks, RING::kWarps * 32, smem, st>>>(act_map, tab_map, static_cast<int>(n), static_cast<int>(T), lv->X,
+                                                 words, pos, obs, reward, done, lv->start, env_return, env_done, stats,
+                                                 flags);
   cudaError_t le = cudaGetLastError();
   return le == cudaSuccess ? GU_OK : static_cast<int>(le);
 }
@@ -305,39 +339,50 @@ rollout_nt16_kernel(int64_t N, int64_t T, int cells, const uint16_t* __restrict_
   long long rsum = 0, dcnt = 0;
   if (env < N) {
     int p = pos[env];
-    const int st = __ldg(start);
-    constexpr int U = 8;
-    int abuf[U];
+    const int st = (auto_reset && start_choice == nullptr) ? __ldg(start) : 0;   // lv->start may be NULL otherwise
+    auto step = [&](int a, int64_t t) {
+      const uint32_t v = tab[p * 4 + (a & 3)];
+      const int n = static_cast<int>(v & 0x3fffu);
+      const bool lava = v & 0x8000u, goal = v & 0x4000u;
+      const int r = lava ? kRewardLava : (goal ? kRewardGoal : kRewardStep);
+      const bool d = lava | goal;
+      if (TRAJ) {
+        const int64_t o = t * N + env;
+        if (obs) obs[o] = n;
+        if (reward) reward[o] = r;
+        if (done) done[o] = d;
+      }
+      rsum += r;
+      dcnt += d ? 1 : 0;
+      p = n;
+      if (auto_reset && d) p = start_choice != nullptr ? __ldg(start_choice + t * N + env) : st;
+    };
+    if (flags & GU_FLAG_PACKED_ACTIONS) {            // 16 steps per word, next word loaded a word ahead
+      const int64_t nw = (T + 15) / 16;
+      uint32_t next = static_cast<uint32_t>(__ldg(actions + env));
+      for (int64_t wq = 0; wq < nw; ++wq) {
+        const uint32_t w = next;
+        if (wq + 1 < nw) next = static_cast<uint32_t>(__ldg(actions + (wq + 1) * N + env));
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-      if (u < T) abuf[u] = __ldg(actions + static_cast<int64_t>(u) * N + env);
-    for (int64_t t0 = 0; t0 < T; t0 += U) {
-      int acur[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) acur[u] = abuf[u];
+        for (int s16 = 0; s16 < 16; ++s16)
+          if (wq * 16 + s16 < T) step(static_cast<int>((w >> (2 * s16)) & 3u), wq * 16 + s16);
+      }
+    } else {
+      constexpr int U = 8;
+      int abuf[U];
 #pragma unroll
       for (int u = 0; u < U; ++u)
-        if (t0 + U + u < T) abuf[u] = __ldg(actions + (t0 + U + u) * N + env);
+        if (u < T) abuf[u] = __ldg(actions + static_cast<int64_t>(u) * N + env);
+      for (int64_t t0 = 0; t0 < T; t0 += U) {
+        int acur[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int64_t t = t0 + u;
-        if (t < T) {
-          const uint32_t v = tab[p * 4 + (acur[u] & 3)];
-          const int n = static_cast<int>(v & 0x3fffu);
-          const bool lava = v & 0x8000u, goal = v & 0x4000u;
-          const int r = lava ? kRewardLava : (goal ? kRewardGoal : kRewardStep);
-          const bool d = lava | goal;
-          if (TRAJ) {
-            const int64_t o = t * N + env;
-            if (obs) obs[o] = n;
-            if (reward) reward[o] = r;
-            if (done) done[o] = d;
-          }
-          rsum += r;
-          dcnt += d ? 1 : 0;
-          p = n;
-          if (auto_reset && d) p = start_choice != nullptr ? __ldg(start_choice + t * N + env) : st;
-        }
+        for (int u = 0; u < U; ++u) acur[u] = abuf[u];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (t0 + U + u < T) abuf[u] = __ldg(actions + (t0 + U + u) * N + env);
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (t0 + u < T) step(acur[u], t0 + u);
       }
     }
     pos[env] = p;
@@ -357,6 +402,7 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
   const TableFormat fmt = table_format(lv);
   const int cells = lv->X * lv->Y;
   const bool traj = obs || reward || done;
+  const bool packed = flags & GU_FLAG_PACKED_ACTIONS;
   if (fmt == kTableINFO8) {
     if (start_choice != nullptr || !al16(actions) || !al16(tables) || n % 32 != 0 || n >= (1ll << 31))
       return GU_ERR_UNSUPPORTED;
@@ -364,19 +410,33 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
     // batches), else 1 so small batches spread over all SMs; 4 only on request
     static const char* force = getenv("GU_INFO8_EPT");
     int ept = (n % 64 == 0 && n / 64 >= 148 * 12) ? 2 : 1;
-    if (force) ept = atoi(force);
+    if (force && (atoi(force) == 1 || atoi(force) == 2 || atoi(force) == 4)) ept = atoi(force);   // developer switch
     if (n % (32 * ept) != 0) return GU_ERR_UNSUPPORTED;
     const bool ar = flags & GU_FLAG_AUTO_RESET;
+    // small batches (about one resident wave of warps): deep ring, two warps per block
+    static const char* ring_env = getenv("GU_INFO8_RING");        // developer switch: "std" / "deep"
+    bool deep = ept == 1 && n / 32 <= 148 * 24 && info8_smem_bytes<RingDeep>((cells + 3) / 4, 1) <= 100 * 1024;
+    if (ring_env) deep = ept == 1 && ring_env[0] == 'd';
 #define GU_INFO8_ARGS lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats, tables, flags, st
-#define GU_INFO8(EPT)                                                                              \
-  return traj ? (ar ? launch_info8<EPT, true, true>(GU_INFO8_ARGS)                                 \
-                    : launch_info8<EPT, true, false>(GU_INFO8_ARGS))                               \
-              : (ar ? launch_info8<EPT, false, true>(GU_INFO8_ARGS)                                \
-                    : launch_info8<EPT, false, false>(GU_INFO8_ARGS))
-    if (ept == 4) GU_INFO8(4);
-    if (ept == 2) GU_INFO8(2);
-    GU_INFO8(1);
+#define GU_INFO8_P(EPT, RING, PACKED)                                                                 \
+  return traj ? (ar ? launch_info8<EPT, true, true, RING, PACKED>(GU_INFO8_ARGS)                      \
+                    : launch_info8<EPT, true, false, RING, PACKED>(GU_INFO8_ARGS))                    \
+              : (ar ? launch_info8<EPT, false, true, RING, PACKED>(GU_INFO8_ARGS)                     \
+                    : launch_info8<EPT, false, false, RING, PACKED>(GU_INFO8_ARGS))
+#define GU_INFO8(EPT, RING)            \
+  do {                                 \
+    if (packed) {                      \
+      GU_INFO8_P(EPT, RING, true);     \
+    } else {                           \
+      GU_INFO8_P(EPT, RING, false);    \
+    }                                  \
+  } while (0)
+    if (ept == 4) GU_INFO8(4, RingStd);
+    if (ept == 2) GU_INFO8(2, RingStd);
+    if (deep) GU_INFO8(1, RingDeep);
+    GU_INFO8(1, RingStd);
 #undef GU_INFO8
+#undef GU_INFO8_P
 #undef GU_INFO8_ARGS
   }
   if (fmt == kTableNT16) {

@@ -6,7 +6,7 @@
 // sequentially over episodes.  To stay bit-exact the device keeps exactly that order:
 // one thread per visit index for G (sequential in i), one thread per state for the
 // accumulation over visit indices (sequential in idx).  fp64, no fused multiply-add.
-#include "gu_common.cuh"
+#include "gu_env.cuh"
 
 namespace gu {
 
@@ -71,9 +71,123 @@ mc_finalize_kernel(int cells, const double* __restrict__ total_visits,
   if (total_visits[s] > 0.0) value[s] = __ddiv_rn(total_return[s], total_visits[s]);   // :93-97
 }
 
+// ---- a whole batch of episodes in one launch ------------------------------------------------------
+// monte_carlo_evaluation's loop (monte_carlo.py:49-91) for E episodes: the episodes are sequential by
+// nature -- episode e consumes the uniform draws that follow episode e-1's, and V is folded episode
+// by episode -- so one thread block walks them in order: thread 0 plays the episode
+// (run_episode, :7-26), then all threads compute the truncated returns (one visit index each) and
+// the per-state accumulation / update, in exactly the order of mc_returns_kernel / mc_update_kernel.
+// No host round trip per episode; the host reads the lengths, done flags and the number of draws
+// consumed once per launch.
+constexpr int kMcThreads = 256;
+
+__global__ void __launch_bounds__(kMcThreads)
+mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* __restrict__ uniforms,
+                   long long n_uniforms, const int32_t* __restrict__ starts, int E, int T,
+                   const double* __restrict__ weights, const uint8_t* __restrict__ keep, int every_visit, int mode,
+                   double alpha, int cells, int32_t* __restrict__ obs, int32_t* __restrict__ rew,
+                   double* __restrict__ G, double* __restrict__ total_visits, double* __restrict__ total_return,
+                   double* __restrict__ value, int32_t* __restrict__ lengths, uint8_t* __restrict__ done,
+                   long long* __restrict__ meta) {
+  __shared__ int L_sh, stop_sh;
+  __shared__ long long off_sh;
+  const int tid = threadIdx.x;
+  if (tid == 0) { off_sh = 0; stop_sh = 0; }
+  __syncthreads();
+  int e = 0;
+  for (; e < E; ++e) {
+    const int start = __ldg(starts + e);
+    if (tid == 0) {
+      int s = start, t = 0;
+      bool d = false;
+      const long long off = off_sh;
+      for (; t < T && !d; ++t) {
+        if (off + t >= n_uniforms) { stop_sh = 1; break; }            // out of draws: the host continues
+        const double* row = cdf + static_cast<int64_t>(s) * 4;
+        if (__ldg(row + 3) != __ldg(row + 3)) { stop_sh = 2 + s; break; }   // np.random.choice would raise here
+        const double u = __ldg(uniforms + off + t);
+        const int a = (__ldg(row) <= u) + (__ldg(row + 1) <= u) + (__ldg(row + 2) <= u);
+        int n, r;
+        transition(lv, 0, s, a, true, n, r, d);
+        obs[t] = n;
+        rew[t] = r;
+        s = n;
+      }
+      if (stop_sh == 0) {
+        L_sh = t;
+        off_sh = off + t;
+        lengths[e] = t;
+        done[e] = d;
+      } else if (stop_sh >= 2) {
+        off_sh = off + t;                       // draws consumed before the failing step
+      }
+    }
+    __syncthreads();
+    if (stop_sh != 0) break;
+    const int L = L_sh;
+    for (int idx = tid; idx <= L; idx += kMcThreads) {                 // G[idx] (:69-70)
+      double acc = 0.0;
+      const int n = L - idx;
+      for (int i = 0; i < n; ++i)
+        if (__ldg(keep + i)) acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + i), static_cast<double>(rew[idx + i])));
+      G[idx] = acc;
+    }
+    __syncthreads();
+    for (int s = tid; s < cells; s += kMcThreads) {                    // per state (:56-91)
+      double visits = 0.0, ret = 0.0;
+      for (int idx = 0; idx <= L; ++idx) {
+        if ((idx == 0 ? start : obs[idx - 1]) != s) continue;
+        if (visits != 0.0 && !every_visit) continue;
+        visits = __dadd_rn(visits, 1.0);
+        ret = __dadd_rn(ret, G[idx]);
+      }
+      const double tv = __dadd_rn(total_visits[s], visits);
+      total_visits[s] = tv;
+      if (mode == 2) {
+        total_return[s] = __dadd_rn(total_return[s], ret);
+      } else if (mode == 0) {
+        if (tv > 0.0) {
+          const double v = value[s];
+          value[s] = __dadd_rn(v, __dmul_rn(__ddiv_rn(1.0, tv), __dadd_rn(ret, -v)));
+        }
+      } else {
+        const double v = value[s];
+        value[s] = __dadd_rn(v, __dmul_rn(alpha, __dadd_rn(ret, -v)));
+      }
+    }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    meta[0] = e;                 // episodes completed
+    meta[1] = off_sh;            // uniform draws consumed
+    meta[2] = stop_sh;           // 0 ok, 1 out of draws, 2 + s: state s has an unnormalisable policy row
+    meta[3] = e > 0 ? (L_sh > 0 ? obs[L_sh - 1] : __ldg(starts + e - 1)) : -1;   // where the last episode ended
+  }
+}
+
 }  // namespace gu
 
 using namespace gu;
+
+extern "C" __attribute__((visibility("default"))) int gu_mc_evaluate_f64(
+    const gu_levels* lv, const double* cdf, const double* uniforms, int64_t n_uniforms, const int32_t* starts,
+    int32_t n_episodes, int32_t max_steps, const double* weights, const uint8_t* keep, int32_t every_visit,
+    int32_t mode, double alpha, int32_t* obs_scratch, int32_t* rew_scratch, double* g_scratch, double* total_visits,
+    double* total_return, double* value, int32_t* lengths, uint8_t* done, int64_t* meta, void* stream) {
+  int rc = check_levels(lv, 1);
+  if (rc) return rc;
+  if (lv->per_env) return GU_ERR_UNSUPPORTED;
+  if (!cdf || !uniforms || !starts || !weights || !keep || !obs_scratch || !rew_scratch || !g_scratch || !total_visits ||
+      !total_return || !value || !lengths || !done || !meta)
+    return GU_ERR_NULL;
+  if (n_episodes < 0 || max_steps < 0 || n_uniforms < 0 || mode < 0 || mode > 2) return GU_ERR_SHAPE;
+  mc_evaluate_kernel<<<1, kMcThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+      view_of(lv, 1), cdf, uniforms, n_uniforms, starts, n_episodes, max_steps, weights, keep, every_visit, mode, alpha,
+      lv->X * lv->Y, obs_scratch, rew_scratch, g_scratch, total_visits, total_return, value, lengths, done,
+      reinterpret_cast<long long*>(meta));
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
 
 extern "C" __attribute__((visibility("default"))) int gu_mc_episode_f64(
     int32_t cells, int32_t episode_len, const int32_t* start, const int32_t* obs,

@@ -121,6 +121,7 @@ class EnvLevels(object):
     def ref(self):
         return ctypes.byref(self.desc)
 
+    @_cabi.on_device
     def build_tables(self, n_envs, flags=0):
         """Build the transition tables of the table-driven rollout kernels (if the shape has one)."""
         L = _cabi.lib()
@@ -161,6 +162,7 @@ class PlanGrid(object):
         self.wall, self.goal, self.lava = planes
         self.finish()
 
+    @_cabi.on_device
     def finish(self):
         """Build the descriptor and the derived `info` plane (gu_pack_info) the tiled kernels read."""
         self.desc = _cabi.GuGrid(self.X, self.Y, self.row_begin, self.row_end, self.pitch, self.pitch_words,

@@ -61,6 +61,7 @@ class GridUniverseVecEnv(object):
         self.stats = torch.zeros(2, dtype=torch.int64, device=self.device)   # [reward sum, done count]
         self._lib = _cabi.lib()
         self._pinned = {}
+        self._pin_events = {}
         if use_tables:
             self.levels.build_tables(self.num_envs)
         self.reset()
@@ -85,15 +86,57 @@ class GridUniverseVecEnv(object):
         if is_action and a.size and (a.max() > 3 or a.min() < -4):
             raise IndexError("list index out of range")   # what the reference's action list raises
         stage = self._pin(name, a.shape, torch.int32)
+        ev = self._pin_events.get(name)
+        if ev is not None:
+            ev.synchronize()                 # the previous copy out of this staging buffer has finished
         stage.numpy()[...] = a
-        return stage.to(self.device, non_blocking=True)
+        out = stage.to(self.device, non_blocking=True)
+        ev = self._pin_events[name] = torch.cuda.Event()
+        ev.record()
+        return out
+
+    @staticmethod
+    def _check_device_actions(a):
+        """Device-side twin of the host range check (one reduction + one sync): the kernels use only
+        the two low bits of an action, so 4 would silently act as UP where the reference raises."""
+        if a.numel() and bool(((a > 3) | (a < -4)).any()):
+            raise IndexError("list index out of range")
+
+    @_cabi.on_device
+    def pack_actions(self, actions, threads=0, out=None):
+        """int32 actions [T, N] -> the packed stream of GU_FLAG_PACKED_ACTIONS (2 bits per step, 16
+        steps per word, [ceil(T/16), N]).  A device tensor is packed on the device, a host array /
+        pinned tensor on the host cores (gu_pack_actions_host; ``out``: a pinned int32 tensor to
+        reuse).  Returns (packed, T)."""
+        if torch.is_tensor(actions) and actions.is_cuda:
+            assert actions.dtype == torch.int32 and actions.dim() == 2 and actions.is_contiguous()
+            T, n = int(actions.shape[0]), int(actions.shape[1])
+            out = torch.empty(((T + 15) // 16, n), dtype=torch.int32, device=actions.device)
+            _cabi.check("gu_pack_actions", self._lib.gu_pack_actions(_cabi.ptr(actions), T, n, _cabi.ptr(out),
+                                                                     _cabi.stream_ptr()))
+            return out, T
+        src = actions if torch.is_tensor(actions) else torch.from_numpy(np.ascontiguousarray(actions, dtype=np.int32))
+        assert src.dtype == torch.int32 and src.dim() == 2 and src.is_contiguous()
+        T, n = int(src.shape[0]), int(src.shape[1])
+        if out is None:
+            out = torch.empty(((T + 15) // 16, n), dtype=torch.int32, pin_memory=True)
+        assert out.dtype == torch.int32 and tuple(out.shape) == ((T + 15) // 16, n) and out.is_contiguous()
+        _cabi.check("gu_pack_actions_host", self._lib.gu_pack_actions_host(
+            ctypes.c_void_p(src.data_ptr()), T, n, ctypes.c_void_p(out.data_ptr()), int(threads)))
+        return out, T
 
     # ------------------------------------------------------------------ API
+    @_cabi.on_device
     def reset(self, start_states=None):
         """Put every env on its start state (griduniverse_env.py:187-193).  With several start
         states in a shared level the choice is uniform per env (host RNG, numpy)."""
         if start_states is not None:
-            self.pos.copy_(torch.as_tensor(np.asarray(start_states, dtype=np.int32)).to(self.device))
+            t = start_states if torch.is_tensor(start_states) else torch.as_tensor(np.asarray(start_states, dtype=np.int32))
+            t = t.to(device=self.device, dtype=torch.int32).reshape(-1)
+            # the kernels index the level tables with these: an out-of-range state would read past them
+            if t.numel() != self.num_envs or bool(((t < 0) | (t >= self.x_max * self.y_max)).any()):
+                raise IndexError("start_states must hold num_envs states in [0, %d)" % (self.x_max * self.y_max))
+            self.pos.copy_(t)
         elif self.levels.per_env:
             self.pos.copy_(self.levels.start)
         else:
@@ -106,12 +149,17 @@ class GridUniverseVecEnv(object):
         self.stats.zero_()
         return self.pos.clone()
 
-    def step(self, actions, start_choice=None):
+    @_cabi.on_device
+    def step(self, actions, start_choice=None, validate=False):
         """One step for all envs.  Device tensor in -> device tensors out; host array in ->
-        NumPy arrays out.  Returns (obs, reward, done, info)."""
+        NumPy arrays out.  Returns (obs, reward, done, info).  Host actions outside 0..3 raise like
+        the reference's action list (-1..-4 wrap like its negative index); device tensors are only
+        checked with ``validate=True`` (the kernels use the two low bits)."""
         host = not torch.is_tensor(actions)
         a = self._to_device_i32(actions, "actions", True) if host else actions
         assert a.dtype == torch.int32 and a.numel() == self.num_envs
+        if validate and not host:
+            self._check_device_actions(a)
         sc = None
         if start_choice is not None:
             sc = self._to_device_i32(start_choice, "start_choice") if not torch.is_tensor(start_choice) \
@@ -135,17 +183,31 @@ class GridUniverseVecEnv(object):
         torch.cuda.current_stream().synchronize()
         return h_obs.numpy().copy(), h_rew.numpy().copy(), h_done.numpy().astype(bool), {}
 
-    def rollout(self, actions, trajectories=False, start_choice=None, per_env=True):
-        """T steps in one launch.  ``actions`` int32 [T, N] (device tensor or host array).
+    @_cabi.on_device
+    def rollout(self, actions, trajectories=False, start_choice=None, per_env=True, packed_steps=None,
+                validate=False):
+        """T steps in one launch.  ``actions`` int32 [T, N] (device tensor or host array), or -- with
+        ``packed_steps=T`` -- the packed stream [ceil(T/16), N] made by ``pack_actions``.
+        ``validate=True`` range-checks device-resident actions like the host path does (one extra
+        reduction and a sync; off by default: the kernels use the two low bits).
 
         Returns a dict: ``pos`` (final), ``env_return`` / ``env_done`` per env, ``stats``
         (int64 [reward sum, done count] accumulated since reset) and, with
         ``trajectories=True``, ``obs`` / ``reward`` / ``done`` [T, N].  Host input gives NumPy
         outputs (copied back through pinned memory)."""
         host = not torch.is_tensor(actions)
-        a = self._to_device_i32(actions, "roll_actions", True) if host else actions
+        a = self._to_device_i32(actions, "roll_actions", packed_steps is None) if host else actions
+        if a.device != self.device:
+            a = a.to(self.device, non_blocking=True)
         assert a.dtype == torch.int32 and a.dim() == 2 and a.shape[1] == self.num_envs and a.is_contiguous()
+        if validate and not host and packed_steps is None:
+            self._check_device_actions(a)
         T, n = int(a.shape[0]), self.num_envs
+        flags = self._flags()
+        if packed_steps is not None:
+            T = int(packed_steps)
+            assert a.shape[0] == (T + 15) // 16, "packed action stream needs ceil(T/16) rows"
+            flags |= _cabi.GU_FLAG_PACKED_ACTIONS
         sc = None
         if start_choice is not None:
             sc = self._to_device_i32(start_choice, "roll_start_choice") if not torch.is_tensor(start_choice) \
@@ -161,7 +223,7 @@ class GridUniverseVecEnv(object):
         rc = self._lib.gu_rollout(self.levels.ref(), n, T, _cabi.ptr(a), _cabi.ptr(self.pos), _cabi.ptr(obs),
                                   _cabi.ptr(reward), _cabi.ptr(done), _cabi.ptr(sc), _cabi.ptr(env_ret),
                                   _cabi.ptr(env_done), _cabi.ptr(self.stats), _cabi.ptr(self.levels.tables),
-                                  self._flags(), _cabi.stream_ptr())
+                                  flags, _cabi.stream_ptr())
         _cabi.check("gu_rollout", rc)
         self.launches = getattr(self, "launches", 0) + 1
         out = {"pos": self.pos, "env_return": env_ret, "env_done": env_done, "stats": self.stats,
@@ -179,6 +241,7 @@ class GridUniverseVecEnv(object):
         torch.cuda.current_stream().synchronize()
         return {k: (None if v is None else v.numpy().copy()) for k, v in res.items()}
 
+    @_cabi.on_device
     def render_ansi(self, envs=None):
         """render(mode='ansi') of the whole batch in one launch (griduniverse_env.py:202-221):
         a list of strings, one frame per env (or for the given env indices only)."""
@@ -191,9 +254,11 @@ class GridUniverseVecEnv(object):
             text = text[torch.as_tensor(list(envs), device=self.device, dtype=torch.long)]
         return [bytes(row).decode("ascii") for row in text.cpu().numpy()]
 
-    def rollout_stream(self, slabs):
+    @_cabi.on_device
+    def rollout_stream(self, slabs, packed_steps=None):
         """Streamed rollout from HOST memory: ``slabs`` is an iterable of pinned int32 host
-        tensors [t_i, N] (consecutive time slices of the action stream).  Each slab is copied
+        tensors [t_i, N] (consecutive time slices of the action stream); with ``packed_steps=k`` every
+        slab is a packed stream of k steps ([ceil(k/16), N], see ``pack_actions``).  Each slab is copied
         host->device on a side stream into one of two device buffers while the kernel works on
         the previous slab; per-env returns / done counts accumulate across slabs.  Returns NumPy
         ``pos``, ``env_return``, ``env_done`` and ``stats`` (device->host through pinned memory)."""
@@ -212,9 +277,12 @@ class GridUniverseVecEnv(object):
         for i, slab in enumerate(slabs):
             assert slab.dtype == torch.int32 and slab.dim() == 2 and slab.shape[1] == n
             b, t = i % 2, int(slab.shape[0])
+            steps = t if packed_steps is None else int(packed_steps)
             buf = self._slab_bufs[b]
             if buf is None or buf.shape[0] < t:
-                buf = self._slab_bufs[b] = torch.empty((t, n), dtype=torch.int32, device=self.device)
+                with torch.cuda.stream(copy):       # allocated on the stream that writes it; the kernel's
+                    buf = self._slab_bufs[b] = torch.empty((t, n), dtype=torch.int32, device=self.device)
+                buf.record_stream(main)             # use on the main stream is declared to the allocator
             with torch.cuda.stream(copy):
                 if i >= 2:
                     copy.wait_event(free[b])
@@ -222,10 +290,12 @@ class GridUniverseVecEnv(object):
                 ready[b].record(copy)
             h2d += slab.numel() * 4
             main.wait_event(ready[b])
-            rc = self._lib.gu_rollout(self.levels.ref(), n, t, _cabi.ptr(buf), _cabi.ptr(self.pos), None, None,
+            flags = self._flags() | _cabi.GU_FLAG_ACCUMULATE
+            if packed_steps is not None:
+                flags |= _cabi.GU_FLAG_PACKED_ACTIONS
+            rc = self._lib.gu_rollout(self.levels.ref(), n, steps, _cabi.ptr(buf), _cabi.ptr(self.pos), None, None,
                                       None, None, _cabi.ptr(env_ret), _cabi.ptr(env_done), _cabi.ptr(self.stats),
-                                      _cabi.ptr(self.levels.tables), self._flags() | _cabi.GU_FLAG_ACCUMULATE,
-                                      _cabi.stream_ptr(main))
+                                      _cabi.ptr(self.levels.tables), flags, _cabi.stream_ptr(main))
             _cabi.check("gu_rollout", rc)
             free[b].record(main)
             self.launches = getattr(self, "launches", 0) + 1
@@ -240,6 +310,7 @@ class GridUniverseVecEnv(object):
         res["d2h_bytes"] = sum(v.numel() * v.element_size() for v in out.values())
         return res
 
+    @_cabi.on_device
     def look_step_ahead(self, states, actions, care_about_terminal=True):
         """Batched look_step_ahead (griduniverse_env.py:136-155) -> (next, reward, terminal).
         Shared level: any number of pairs; per-env levels: pair i is evaluated on level i."""

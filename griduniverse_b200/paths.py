@@ -30,6 +30,7 @@ class ShortestPaths(object):
         self.reached = 0      # cells with a distance (sources included)
         self.launches = 0
 
+    @_cabi.on_device
     def source_plane(self, states):
         """Bit plane (device) with the given dense state indices set."""
         g = self.grid
@@ -38,6 +39,7 @@ class ShortestPaths(object):
         words = pack_grid_plane(mask.reshape(g.Y, g.X), 0, g.Y, g.pitch_words)
         return torch.from_numpy(words.view(np.int32).reshape(-1)).to(self.device)
 
+    @_cabi.on_device
     def solve(self, sources=None, lava_blocks=False, max_levels=None):
         """Run the wavefront to exhaustion.  ``sources``: None (the goal cells), an iterable of
         state indices, or a device bit plane.  Returns the padded int32 distance tensor
@@ -70,6 +72,7 @@ class ShortestPaths(object):
         self.levels = int(self.dist.max().item()) if total else 0
         return self.dist
 
+    @_cabi.on_device
     def walk(self, start_state, max_len=None):
         """Action list of a shortest path from ``start_state`` to the nearest source of the last
         ``solve`` (None if it was not reached)."""

@@ -54,6 +54,7 @@ class Planner(object):
         self.launches = 0
 
     # ------------------------------------------------------------------ policy staging
+    @_cabi.on_device
     def stage_policy(self, policy):
         """Caller's policy -> (kind, device tensor or None).
 
@@ -75,6 +76,7 @@ class Planner(object):
         return _cabi.GU_POLICY_PROBS, self.grid.pad(pol.astype(self.np_dtype), self.dtype)
 
     # ------------------------------------------------------------------ kernels
+    @_cabi.on_device
     def sweep(self, v_in, v_out, kind, policy_t, gamma, residual=None, gate=None, threshold=0.0):
         rc = self._sweep_fn(self.grid.ref(), _cabi.ptr(v_in), _cabi.ptr(v_out), kind, _cabi.ptr(policy_t),
                             float(gamma), _cabi.ptr(residual), _cabi.ptr(gate), float(threshold),
@@ -82,6 +84,7 @@ class Planner(object):
         _cabi.check("gu_sweep", rc)
         self.launches += 1
 
+    @_cabi.on_device
     def greedy(self, v, gamma, out=None):
         out = self.grid.empty(torch.uint8) if out is None else out
         rc = self._greedy_fn(self.grid.ref(), _cabi.ptr(v), _cabi.ptr(out), float(gamma), _cabi.stream_ptr())
@@ -89,6 +92,7 @@ class Planner(object):
         self.launches += 1
         return out
 
+    @_cabi.on_device
     def max_diff(self, a, b):
         """Signed max of (a - b) over the owned cells as a device scalar (dynamic_programming.py:44)."""
         out = self.new_residuals(1)
@@ -100,6 +104,7 @@ class Planner(object):
     def new_residuals(self, n):
         return torch.full((n,), float("-inf"), dtype=self.dtype, device=self.device)
 
+    @_cabi.on_device
     def stage_value(self, value_function):
         if value_function is None:
             return self.grid.empty()
@@ -108,6 +113,7 @@ class Planner(object):
         return self.grid.pad(value_function)
 
     # ------------------------------------------------------------------ value iteration
+    @_cabi.on_device
     def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
                         discount_factor=1.0, chunk=16, allow_small=True, use_graph=True):
         """dynamic_programming.py:8-28.  Returns (V_padded, tie_masks_padded, sweeps, last_delta).
@@ -140,6 +146,7 @@ class Planner(object):
         return v.clone(), tie, sweeps, last      # v is a view of the driver's persistent buffers
 
     # ------------------------------------------------------------------ policy iteration
+    @_cabi.on_device
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
                          discount_factor=1.0, allow_small=True, chunk=16, use_graph=True):
         """dynamic_programming.py:31-57.  Returns (V_lastconv_padded, tie_masks or None, sweeps,

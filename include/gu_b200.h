@@ -58,6 +58,9 @@ typedef struct {
 #define GU_FLAG_AUTO_RESET 1u      /* after a done step the env continues from its start state */
 #define GU_FLAG_NO_CARE_TERMINAL 2u /* care_about_terminal=False (griduniverse_env.py:150-153) */
 #define GU_FLAG_ACCUMULATE 4u      /* gu_rollout: env_return / env_done += instead of = (streamed slabs) */
+#define GU_FLAG_PACKED_ACTIONS 8u  /* gu_rollout: `actions` holds 2 bits per step, 16 steps per 32-bit word:
+                                    * uint32[ceil(T/16)][N], step t of env n in bits 2*(t%16).. of word
+                                    * [t/16][n] -- a sixteenth of the bytes of the int32 stream */
 
 /* One step for N envs: GridUniverseEnv._step (griduniverse_env.py:176-185) =
  * look_step_ahead(current_state, action) (:136-155) for every env.
@@ -88,6 +91,14 @@ int gu_rollout(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const int32
                const int32_t* start_choice, int32_t* env_return, int32_t* env_done,
                int64_t* stats, const uint32_t* tables, uint32_t flags, void* stream);
 
+/* int32 actions [T][N] (two low bits used, like gu_rollout) -> the packed stream of
+ * GU_FLAG_PACKED_ACTIONS, uint32[ceil(T/16)][N].  gu_pack_actions: device pointers, enqueued on
+ * `stream`.  gu_pack_actions_host: HOST pointers, runs on n_threads CPU threads (0 = all cores) and
+ * returns when done -- for callers whose action source is a host int32 array. */
+int gu_pack_actions(const int32_t* actions, int64_t n_steps, int64_t n_envs, uint32_t* packed, void* stream);
+int gu_pack_actions_host(const int32_t* actions, int64_t n_steps, int64_t n_envs, uint32_t* packed,
+                         int32_t n_threads);
+
 /* Policy-driven episodes: run_episode (core/algorithms/monte_carlo.py:7-26) for N
  * episodes on one SHARED level, the randomness host-supplied as uniform draws.
  *   cdf      f64[cells][4]  cumulative action probabilities per state, built exactly like
@@ -97,7 +108,9 @@ int gu_rollout(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const int32
  *   pos      int32[N]       in: start states, out: final states
  *   obs int32[T][N], reward int32[T][N] trajectories (entries past an episode's end are
  *   left untouched), length int32[N] = steps taken (<= T), done uint8[N]; any may be NULL.
- * An episode stops at its first done step (monte_carlo.py:24-25). */
+ * An episode stops at its first done step (monte_carlo.py:24-25).  A cdf row of NaN marks a state
+ * whose probabilities np.random.choice would reject: an episode that has to sample there stops with
+ * length = -1 - (steps taken) and done = 0. */
 int gu_rollout_policy(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const double* cdf,
                       const double* uniforms, int32_t* pos, int32_t* obs, int32_t* reward,
                       int32_t* length, uint8_t* done, void* stream);
@@ -119,6 +132,21 @@ int gu_mc_episode_f64(int32_t cells, int32_t episode_len, const int32_t* start, 
                       const uint8_t* keep, int32_t every_visit, int32_t mode, double alpha,
                       double* g_scratch, double* total_visits, double* total_return, double* value,
                       void* stream);
+/* monte_carlo_evaluation's episode loop (monte_carlo.py:49-91) for n_episodes episodes on one SHARED
+ * level in ONE launch: episode e starts in starts[e] (the host's random.choice, griduniverse_env.py:189),
+ * takes its actions from the uniform draws that follow episode e-1's (uniforms f64[n_uniforms], one
+ * stream for the whole batch, consumed exactly like np.random.choice would, :20), and is folded into
+ * total_visits / total_return / value like gu_mc_episode_f64 does, episode after episode.
+ *   obs_scratch / rew_scratch int32[max_steps], g_scratch f64[max_steps + 1]
+ *   lengths int32[n_episodes], done uint8[n_episodes]: per-episode results
+ *   meta int64[4]: episodes completed, draws consumed, status (0 ok; 1 ran out of draws; 2 + s: state
+ *   s was visited and its cdf row is NaN = np.random.choice would raise ValueError there), state the
+ *   last completed episode ended in.  Everything device memory. */
+int gu_mc_evaluate_f64(const gu_levels* lv, const double* cdf, const double* uniforms, int64_t n_uniforms,
+                       const int32_t* starts, int32_t n_episodes, int32_t max_steps, const double* weights,
+                       const uint8_t* keep, int32_t every_visit, int32_t mode, double alpha, int32_t* obs_scratch,
+                       int32_t* rew_scratch, double* g_scratch, double* total_visits, double* total_return,
+                       double* value, int32_t* lengths, uint8_t* done, int64_t* meta, void* stream);
 /* V(s) = S(s) / N(s) where N(s) > 0 (monte_carlo.py:93-97). */
 int gu_mc_finalize_f64(int32_t cells, const double* total_visits, const double* total_return,
                        double* value, void* stream);

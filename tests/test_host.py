@@ -156,6 +156,16 @@ def test_choice_cdf_reproduces_numpy_choice():
     got = [(cdf[s, :3] <= u[i]).sum() for i, s in enumerate(states)]
     assert expect == got
     assert np.random.random_sample() == np.random.RandomState(11).random_sample(201)[-1]
+    # rows RandomState.choice rejects are marked (the kernels stop there, the wrapper raises ValueError)
+    bad = np.array([[0, 0, 0, 0], [0.5, 0.6, 0, 0], [-0.1, 0.6, 0.5, 0], [0.25, 0.25, 0.25, 0.25 + 1e-9], [1, 0, 0, 0]])
+    marked = np.isnan(_choice_cdf(bad)).any(axis=1)
+    for row, m in zip(bad, marked):
+        try:
+            np.random.choice(4, p=row)
+            raised = False
+        except ValueError:
+            raised = True
+        assert raised == bool(m)
 
 
 def test_product_fails_loudly_without_cuda():
