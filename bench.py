@@ -289,24 +289,17 @@ def run_ours(args):
         lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
         env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
         a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev, generator=gen)
-        flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.int32, device=dev)
         for _ in range(W):
             env3.rollout(a3, per_env=True)
-        torch.cuda.synchronize()
-        times = []
-        for _ in range(K):
-            flush.fill_(1)                            # 256 MB write: flush the 126 MB L2 between passes
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            env3.rollout(a3, per_env=True)
-            e1.record()
-            torch.cuda.synchronize()
-            times.append(e0.elapsed_time(e1) / 1000.0)
-        t3 = float(np.mean(times))
-        cfg3 = {"workload": "cfg3: 65,536 16x16 envs, T=1024, per-env levels, 1 GPU, L2 flushed between passes",
+        # one pass reads 268 MB of actions (> the 126 MB L2) in a streaming pattern, so back-to-back passes
+        # cannot live off the cache; timing K launches between two events keeps the host's launch latency
+        # (a third of this 0.07 ms kernel) out of the number
+        t3 = timed(lambda: env3.rollout(a3, per_env=True), K) / K
+        cfg3 = {"workload": "cfg3: 65,536 16x16 envs, T=1024, per-env levels, 1 GPU; inputs larger than L2 (268 MB of "
+                            "actions per pass), %d launches back to back" % K,
                 "value": CFG3_N * CFG3_T / t3, "unit": "steps/s", "ms_per_pass": 1000 * t3,
                 "roofline_frac": BYTES_PER_STEP_SUMMARY * CFG3_N * CFG3_T / t3 / 1e9 / peak}
-        del env3, a3, lv3, flush
+        del env3, a3, lv3
         torch.cuda.empty_cache()
 
     # ------------------------------------------------------------------ VI workload (cfg 5)

@@ -233,14 +233,26 @@ pack_actions_kernel(const int32_t* __restrict__ actions, uint32_t* __restrict__ 
 #include <vector>
 
 namespace gu {
-static void pack_rows_host(const int32_t* actions, uint32_t* packed, int64_t T, int64_t N, int64_t w0, int64_t w1) {
-  for (int64_t w = w0; w < w1; ++w) {
+// columns [i0, i1) of every packed row: 16 input rows are read as 16 concurrent streams
+static void pack_cols_host(const int32_t* actions, uint32_t* packed, int64_t T, int64_t N, int64_t i0, int64_t i1) {
+  const int64_t words = (T + 15) / 16;
+  for (int64_t w = 0; w < words; ++w) {
     uint32_t* out = packed + w * N;
+    const int32_t* in = actions + w * 16 * N;
     const int steps = static_cast<int>(T - w * 16 < 16 ? T - w * 16 : 16);
-    for (int64_t i = 0; i < N; ++i) out[i] = static_cast<uint32_t>(actions[w * 16 * N + i]) & 3u;
-    for (int s = 1; s < steps; ++s) {
-      const int32_t* row = actions + (w * 16 + s) * N;
-      for (int64_t i = 0; i < N; ++i) out[i] |= (static_cast<uint32_t>(row[i]) & 3u) << (2 * s);
+    if (steps == 16) {
+      for (int64_t i = i0; i < i1; ++i) {
+        uint32_t word = 0;
+#pragma GCC unroll 16
+        for (int s = 0; s < 16; ++s) word |= (static_cast<uint32_t>(in[s * N + i]) & 3u) << (2 * s);
+        out[i] = word;
+      }
+    } else {
+      for (int64_t i = i0; i < i1; ++i) {
+        uint32_t word = 0;
+        for (int s = 0; s < steps; ++s) word |= (static_cast<uint32_t>(in[s * N + i]) & 3u) << (2 * s);
+        out[i] = word;
+      }
     }
   }
 }
@@ -267,17 +279,19 @@ extern "C" __attribute__((visibility("default"))) int gu_pack_actions_host(const
   if (n_steps < 0 || n_envs < 0) return GU_ERR_SHAPE;
   if (n_steps == 0 || n_envs == 0) return GU_OK;
   if (!actions || !packed) return GU_ERR_NULL;
-  const int64_t words = (n_steps + 15) / 16;
   int nt = n_threads > 0 ? n_threads : static_cast<int>(std::thread::hardware_concurrency());
   if (nt < 1) nt = 1;
-  if (nt > words) nt = static_cast<int>(words);
+  const int64_t chunks = (n_envs + 4095) / 4096;          // at least 16 KB of output per thread
+  if (nt > chunks) nt = static_cast<int>(chunks);
   if (nt == 1) {
-    pack_rows_host(actions, packed, n_steps, n_envs, 0, words);
+    pack_cols_host(actions, packed, n_steps, n_envs, 0, n_envs);
     return GU_OK;
   }
   std::vector<std::thread> pool;
-  for (int k = 0; k < nt; ++k)
-    pool.emplace_back(pack_rows_host, actions, packed, n_steps, n_envs, words * k / nt, words * (k + 1) / nt);
+  for (int k = 0; k < nt; ++k) {
+    const int64_t i0 = (n_envs * k / nt) & ~static_cast<int64_t>(15), i1 = k + 1 == nt ? n_envs : (n_envs * (k + 1) / nt) & ~static_cast<int64_t>(15);
+    pool.emplace_back(pack_cols_host, actions, packed, n_steps, n_envs, i0, i1);
+  }
   for (auto& t : pool) t.join();
   return GU_OK;
 }

@@ -95,10 +95,13 @@ pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
 #define GU_INFO8_STAGES 2
 #endif
 // Ring geometry (template parameters of the kernel): action rows per TMA box, boxes in flight per
-// warp, warps per block.  Large batches use the shallow ring (more resident warps per SM); batches that
-// leave every SM with only a dozen warps use a deep one -- 4 x 16 rows = 8 KB in flight per warp --
-// because then the bytes in flight, not the warp count, bound the achieved bandwidth (BASELINE cfg 3:
-// 65,536 envs = 14 warps per SM, 0.46 of the HBM roofline with the shallow ring).
+// warp, warps per block.  The shallow ring is the default everywhere.  The deep one (4 x 16 rows = 8 KB
+// in flight per warp) was built for batches that leave an SM with only a dozen warps (BASELINE cfg 3:
+// 65,536 envs = 14 warps per SM) on the theory that bytes in flight bound them; measured on B200 it is
+// SLOWER there (0.100 against 0.081 ms): with one env per lane that workload is bound by the dependent
+// chain of a step (position -> table word -> landing cell, ~150 cycles) times 1024 sequential steps, not
+// by bandwidth -- the packed action stream, a sixteenth of the bytes, still takes 0.065 ms.  It stays
+// selectable (GU_INFO8_RING=deep) for experiments.
 struct RingStd { static constexpr int kRows = GU_INFO8_ROWS, kStages = GU_INFO8_STAGES, kWarps = GU_ROLLOUT_WARPS; };
 struct RingDeep { static constexpr int kRows = 16, kStages = 4, kWarps = 2; };
 
@@ -413,10 +416,9 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
     if (force && (atoi(force) == 1 || atoi(force) == 2 || atoi(force) == 4)) ept = atoi(force);   // developer switch
     if (n % (32 * ept) != 0) return GU_ERR_UNSUPPORTED;
     const bool ar = flags & GU_FLAG_AUTO_RESET;
-    // small batches (about one resident wave of warps): deep ring, two warps per block
-    static const char* ring_env = getenv("GU_INFO8_RING");        // developer switch: "std" / "deep"
-    bool deep = ept == 1 && n / 32 <= 148 * 24 && info8_smem_bytes<RingDeep>((cells + 3) / 4, 1) <= 100 * 1024;
-    if (ring_env) deep = ept == 1 && ring_env[0] == 'd';
+    static const char* ring_env = getenv("GU_INFO8_RING");        // developer switch: "deep"
+    const bool deep = ring_env && ring_env[0] == 'd' && ept == 1 &&
+                      info8_smem_bytes<RingDeep>((cells + 3) / 4, 1) <= 100 * 1024;
 #define GU_INFO8_ARGS lv, n, T, actions, pos, obs, reward, done, env_return, env_done, stats, tables, flags, st
 #define GU_INFO8_P(EPT, RING, PACKED)                                                                 \
   return traj ? (ar ? launch_info8<EPT, true, true, RING, PACKED>(GU_INFO8_ARGS)                      \

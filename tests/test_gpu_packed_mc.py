@@ -1,5 +1,5 @@
 """GPU parity: the packed (2-bit) action stream against the int32 contract on every rollout kernel,
-the host / device packers, the deep-ring geometry of the TMA rollout, and Monte-Carlo evaluation
+the host / device packers, input validation, and Monte-Carlo evaluation
 with many episodes per launch (core/algorithms/monte_carlo.py:29-99) against the reference goldens."""
 import random
 
@@ -36,9 +36,9 @@ def test_packers_agree(T, n):
 
 
 @pytest.mark.parametrize("shape,n,T,per_env,tables", [
-    ((8, 8), 4096, 100, True, True),        # TMA rollout, shallow or deep ring by batch size
-    ((8, 8), 131072, 48, True, True),       # large batch: two envs per lane, shallow ring
-    ((16, 16), 2048, 1000, True, True),     # cfg-3 shape: deep ring
+    ((8, 8), 4096, 100, True, True),        # TMA rollout, one env per lane
+    ((8, 8), 131072, 48, True, True),       # large batch: two envs per lane
+    ((16, 16), 2048, 1000, True, True),     # cfg-3 shape
     ((8, 8), 1001, 33, True, True),         # ragged batch: layout-agnostic kernel
     ((12, 9), 512, 70, False, True),        # shared level: NT16 table kernel
     ((8, 8), 640, 37, True, False)])        # tables off: layout-agnostic kernel
@@ -75,9 +75,9 @@ def test_packed_actions_equal_int32_actions(shape, n, T, per_env, tables, auto_r
         assert r2["h2d_bytes"] * 16 == r1["h2d_bytes"]
 
 
-def test_large_batch_shallow_ring_vs_oracle():
-    """More envs than the deep-ring threshold but fewer than two-per-lane needs: one env per lane on
-    the shallow ring (the third geometry of the TMA rollout), replayed through the oracle."""
+def test_large_batch_vs_oracle():
+    """A batch just below the two-envs-per-lane threshold (one env per lane, many waves of warps),
+    every env replayed through the oracle."""
     from oracle import cpu_baseline as cb
     X, Y, n, T = 8, 8, 148 * 24 * 32 + 4096, 40
     wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, seed=0)
