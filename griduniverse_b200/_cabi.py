@@ -22,7 +22,7 @@ GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 
 
 EXPORTS = ("gu_step", "gu_rollout", "gu_pack_actions", "gu_pack_actions_host", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_evaluate_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
            "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_max_diff_f32", "gu_max_diff_f64", "gu_vi_small_f64",
-           "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_vi_batch_f64", "gu_pi_batch_f64", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_version", "gu_arch", "gu_error_string")
+           "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_vi_batch_f64", "gu_pi_batch_f64", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_render_rgb", "gu_version", "gu_arch", "gu_error_string")
 
 
 class GuLevels(ctypes.Structure):
@@ -121,6 +121,7 @@ def lib():
         "gu_pi_batch_f64": (ctypes.c_int, [gbp, p, p, p, ctypes.c_int, p, f64, f64, i32, p, p, p]),
         "gu_pack_level_text": (ctypes.c_int, [p, i64, i32, i32, p, p, p, p, p, p, p]),
         "gu_render_ansi": (ctypes.c_int, [lvp, i64, p, p, p]),
+        "gu_render_rgb": (ctypes.c_int, [lvp, i64, p, p, i32, i32, p, p]),
         "gu_bfs_init": (ctypes.c_int, [gp, p, p, p, p, p, u32, p]),
         "gu_bfs_expand": (ctypes.c_int, [gp, p, p, p, i32, i32, p, u32, p]),
         "gu_bfs_walk": (ctypes.c_int, [gp, p, i64, p, i32, p, p]),

@@ -111,3 +111,80 @@ extern "C" __attribute__((visibility("default"))) int gu_render_ansi(
   GU_CHECK_LAUNCH();
   return GU_OK;
 }
+
+
+// ---- batched headless RGB render ------------------------------------------------------------------
+// The reference's viewer (core/envs/rendering.py:121-135) draws one sprite per cell -- ground, wall,
+// goal or lava -- and the agent's face on top; render_policy_arrows (:159-212) adds, for every
+// non-terminal non-wall cell and every action with probability >= 0.1, a line of round(p * 20) pixels
+// from the tile centre and an arrowhead 10 wide and 5 high at its end (tiles of 32 pixels).  Its
+// 'rgb_array' mode is half-wired (griduniverse_env.py:223-230) and needs a GL window; here the same
+// picture is rasterised directly, flat colours for the sprites, one thread per pixel, all geometry in
+// integer half-pixel units scaled by tile / 32 so that the NumPy twin in the tests agrees bit for bit.
+namespace gu {
+
+__device__ __forceinline__ bool arrow_hit(int along, int perp, int L2, int W2, int H2, int T2) {
+  if (perp < 0) perp = -perp;
+  if (along >= 0 && along <= L2 && perp <= T2) return true;                       // shaft
+  return along >= L2 && along <= L2 + H2 && perp * H2 <= W2 * (L2 + H2 - along);  // head
+}
+
+__global__ void __launch_bounds__(256)
+render_rgb_kernel(const uint32_t* __restrict__ wall, const uint32_t* __restrict__ goal,
+                  const uint32_t* __restrict__ lava, int per_env, long long n, int X, int Y,
+                  const int32_t* __restrict__ pos, const double* __restrict__ policy, int policy_per_env, int tile,
+                  uint8_t* __restrict__ rgb) {
+  const long long W = static_cast<long long>(X) * tile, H = static_cast<long long>(Y) * tile;
+  const long long i = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n * W * H) return;
+  const long long env = i / (W * H);
+  const long long r = i - env * W * H;
+  const int py = static_cast<int>(r / W), px = static_cast<int>(r - static_cast<long long>(py) * W);
+  const int cx = px / tile, cy = py / tile, c = cy * X + cx;
+  const int cells = X * Y;
+  const size_t w = per_env ? static_cast<size_t>(c >> 5) * n + env : (c >> 5);
+  const uint32_t bit = 1u << (c & 31);
+  const bool is_wall = wall[w] & bit, is_lava = lava[w] & bit, is_goal = goal[w] & bit;
+  uint8_t R = 200, G = 200, B = 200;                       // ground
+  if (is_goal) { R = 40; G = 180; B = 60; }
+  if (is_lava) { R = 220; G = 80; B = 20; }
+  if (is_wall) { R = 60; G = 60; B = 60; }
+  // tile-local coordinates in half pixels, origin at the tile centre, y up
+  const int lx = 2 * (px - cx * tile) + 1 - tile, ly = tile - (2 * (py - cy * tile) + 1);
+  if (policy != nullptr && !is_wall && !is_lava && !is_goal) {
+    const double* row = policy + ((policy_per_env ? env * cells : 0) + c) * 4;
+    const int W2 = 5 * tile / 16, H2 = 5 * tile / 16, T2 = tile / 32 > 1 ? tile / 32 : 1;
+    bool hit = false;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      const double p = row[a];
+      if (!(p >= 0.1)) continue;                            // rendering.py:174-176
+      const int L2 = static_cast<int>(rint(p * 20.0)) * tile / 16;
+      const int along = a == 0 ? ly : a == 1 ? lx : a == 2 ? -ly : -lx;
+      const int perp = (a & 1) ? ly : lx;
+      hit = hit || arrow_hit(along, perp, L2, W2, H2, T2);
+    }
+    if (hit) { R = 0; G = 0; B = 0; }
+  }
+  if (pos != nullptr && pos[env] == c && 100 * (lx * lx + ly * ly) <= 49 * tile * tile) { R = 250; G = 210; B = 40; }   // agent
+  uint8_t* out = rgb + 3 * i;
+  out[0] = R; out[1] = G; out[2] = B;
+}
+
+}  // namespace gu
+
+extern "C" __attribute__((visibility("default"))) int gu_render_rgb(
+    const gu_levels* lv, int64_t n, const int32_t* pos, const double* policy, int32_t policy_per_env, int32_t tile,
+    uint8_t* rgb, void* stream) {
+  if (!lv || !lv->wall || !lv->goal || !lv->lava) return GU_ERR_NULL;
+  if (n == 0) return GU_OK;
+  if (!rgb) return GU_ERR_NULL;
+  if (lv->X <= 0 || lv->Y <= 0 || n < 0 || tile < 16 || tile % 16 != 0 || tile > 256) return GU_ERR_SHAPE;
+  const long long pixels = n * static_cast<long long>(lv->X) * lv->Y * tile * tile;
+  const long long blocks = (pixels + 255) / 256;
+  if (blocks > 2147483647LL) return GU_ERR_SHAPE;
+  gu::render_rgb_kernel<<<static_cast<unsigned>(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      lv->wall, lv->goal, lv->lava, lv->per_env, n, lv->X, lv->Y, pos, policy, policy_per_env, tile, rgb);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}

@@ -6,8 +6,10 @@ core/envs/griduniverse_env.py:14-321 of the reference; the transition itself
 single call costs one launch + one stream synchronise (results land in pinned host memory).  There is no CPU transition code in
 this class: without a CUDA device `step` raises.  Use ``GridUniverseVecEnv`` for throughput.
 
-Not carried over: the pyglet viewer (`render(mode='graphic')`, `render_policy_arrows`) --
-GUI, out of scope.  `random_maze=True` works but uses this repo's own
+Not carried over: the pyglet window (`render(mode='graphic')`) -- GUI, out of scope (SURVEY 2,
+rows 7-8).  What the viewer draws is available headless: `render(mode='rgb_array')` and
+`render_policy_arrows(policy)` return RGB arrays rasterised on the GPU (gu_render_rgb).
+`random_maze=True` works but uses this repo's own
 depth-first maze carver, so a given `random.seed` does not reproduce the reference's maze.
 """
 import ctypes
@@ -23,7 +25,7 @@ from ..spaces import Discrete
 
 
 class GridUniverseEnv(object):
-    metadata = {'render.modes': ['human', 'ansi']}
+    metadata = {'render.modes': ['human', 'ansi', 'rgb_array']}
 
     def __init__(self, grid_shape=(4, 4), *, initial_state=0, goal_states=None, lava_states=None, walls=None,
                  custom_world_fp=None, random_maze=False, device="cuda"):
@@ -174,7 +176,19 @@ class GridUniverseEnv(object):
             outfile = StringIO() if mode == 'ansi' else sys.stdout
             outfile.write(text + '\n')
             return outfile
-        raise NotImplementedError("render mode %r: the pyglet viewer is out of scope" % (mode,))
+        if mode == 'rgb_array':                      # half-wired in the reference (griduniverse_env.py:223-230)
+            return self._rgb(None)
+        raise NotImplementedError("render mode %r: the pyglet window is out of scope" % (mode,))
+
+    def _rgb(self, policy, tile=32):
+        vec = self._device_env()
+        vec.pos.fill_(int(self.current_state))
+        return vec.render_rgb(policy, tile=tile)[0].cpu().numpy()
+
+    def render_policy_arrows(self, policy, tile=32):
+        """rendering.py:159-212 without the window: the frame with the policy's arrows as an
+        RGB array [y_max*tile, x_max*tile, 3] (the reference draws into its pyglet viewer)."""
+        return self._rgb(np.asarray(policy, dtype=np.float64), tile)
 
     def seed(self, seed=None):
         self.np_random = np.random.RandomState(seed)

@@ -255,6 +255,24 @@ class GridUniverseVecEnv(object):
         return [bytes(row).decode("ascii") for row in text.cpu().numpy()]
 
     @_cabi.on_device
+    def render_rgb(self, policy=None, tile=16, show_agent=True):
+        """Headless RGB frames of the whole batch in one launch (gu_render_rgb): uint8 tensor
+        [N, Y*tile, X*tile, 3].  ``policy``: None, or action probabilities [cells, 4] (one policy for
+        all envs) / [N, cells, 4] drawn as the arrows of the reference's ``render_policy_arrows``."""
+        n = self.num_envs
+        pol_t, per_env = None, 0
+        if policy is not None:
+            pol_t = torch.as_tensor(np.asarray(policy, dtype=np.float64)).to(self.device).contiguous()
+            cells = self.x_max * self.y_max
+            assert tuple(pol_t.shape) in ((cells, 4), (n, cells, 4))
+            per_env = int(pol_t.dim() == 3)
+        rgb = torch.empty((n, self.y_max * tile, self.x_max * tile, 3), dtype=torch.uint8, device=self.device)
+        rc = self._lib.gu_render_rgb(self.levels.ref(), n, _cabi.ptr(self.pos) if show_agent else None,
+                                     _cabi.ptr(pol_t), per_env, int(tile), _cabi.ptr(rgb), _cabi.stream_ptr())
+        _cabi.check("gu_render_rgb", rc)
+        return rgb
+
+    @_cabi.on_device
     def rollout_stream(self, slabs, packed_steps=None):
         """Streamed rollout from HOST memory: ``slabs`` is an iterable of pinned int32 host
         tensors [t_i, N] (consecutive time slices of the action stream); with ``packed_steps=k`` every

@@ -236,7 +236,12 @@ class ShardedValueIteration(object):
         last = self._last_buffer()
         last.copy_(self._v())
         self._finish_halos(last, 0)
-        tie, total, delta_eval, exhausted = None, 0, float("nan"), False
+        # the tie masks live in one persistent buffer: the sweeps read the policy in place (:43 mutates the
+        # caller's array too) and a captured chunk of sweeps stays valid from solve to solve
+        if getattr(self, "_tie", None) is None:
+            self._tie = pl.grid.empty(torch.uint8)
+        tie, improved = self._tie, False
+        total, delta_eval, exhausted = 0, float("nan"), False
         while total < max_steps:
             n, delta_eval, conv = self._evaluate((kind, pol_t), (kind, pol_t), threshold, discount_factor,
                                                  max_steps - total, chunk, use_graph)
@@ -244,16 +249,18 @@ class ShardedValueIteration(object):
             if conv:                                            # policy evaluation converged (:42)
                 v = self._v()
                 self._finish_halos(v, n)
-                tie = pl.greedy(v, discount_factor, tie)        # in-place policy update (:43, utils.py:69)
+                pl.greedy(v, discount_factor, tie)              # in-place policy update (:43, utils.py:69)
+                improved = True
                 delta = self._max_diff(last, v)                 # :44
                 last.copy_(v)                                   # :45
                 kind, pol_t = _cabi.GU_POLICY_MASK, tie
                 if pl.np_dtype.type(delta) < thr:
                     break
             else:                                               # budget spent mid-evaluation (:48-56)
-                tie = pl.greedy(last, discount_factor, tie)
+                pl.greedy(last, discount_factor, tie)
+                improved = True
                 exhausted = True
-        return last, tie, total, delta_eval, exhausted
+        return last, (tie if improved else None), total, delta_eval, exhausted
 
     def solve_host(self, v0_host, v_out_host, tie_out_host, policy="uniform", **kw):
         """End-to-end solve with HOST buffers (pinned torch tensors holding this rank's owned

@@ -182,6 +182,18 @@ int gu_pack_level_text(const uint8_t* text, int64_t n_levels, int32_t X, int32_t
  * < G < L < #.  `text`: uint8[n][Y*(2X+1)+1]. */
 int gu_render_ansi(const gu_levels* lv, int64_t n, const int32_t* pos, uint8_t* text, void* stream);
 
+/* Batched headless RGB frames: what the reference's viewer draws (core/envs/rendering.py:121-135: one
+ * tile per cell -- ground / wall / goal / lava, the agent on top) and, with `policy`, what
+ * render_policy_arrows adds (:159-212: per non-terminal non-wall cell and action with p >= 0.1 a line of
+ * round(p * 20) pixels from the tile centre plus an arrowhead, for 32-pixel tiles), rasterised without
+ * a GL window (the reference's 'rgb_array' mode is half-wired, griduniverse_env.py:223-230).  Flat
+ * colours stand in for the sprites.
+ *   pos int32[n] or NULL (no agent); policy f64[cells][4] shared, f64[n][cells][4] with
+ *   policy_per_env = 1, or NULL (no arrows); tile = pixels per cell, a multiple of 16;
+ *   rgb uint8[n][Y * tile][X * tile][3], image row 0 = grid row 0. */
+int gu_render_rgb(const gu_levels* lv, int64_t n, const int32_t* pos, const double* policy, int32_t policy_per_env,
+                  int32_t tile, uint8_t* rgb, void* stream);
+
 /* ---- whole-grid planning ------------------------------------------------ */
 
 /* One grid, or one row shard of it, for the sweep / greedy kernels.
