@@ -117,20 +117,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
 
 // PACKED: the action stream holds 2 bits per step, 16 steps per 32-bit word (uint32[ceil(T/16)][N],
 // step t of env n in bits 2*(t % 16) of word [t / 16][n]): a sixteenth of the bytes, the same steps.
-template <int EPT, bool TRAJ, bool AUTO_RESET, typename RING, bool PACKED>
+// SC: the start state an env continues from after a done step comes from a host-supplied stream
+// start_choice[T][N] (the stand-in for random.choice over several 'x' cells, griduniverse_env.py:189),
+// which travels through the same ring as the actions, one box behind each action box.
+template <int EPT, bool TRAJ, bool AUTO_RESET, typename RING, bool PACKED, bool SC>
 __global__ void __launch_bounds__(RING::kWarps * 32)
 rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __grid_constant__ CUtensorMap tab_map,
-                         int N, int T, int X, int words, int32_t* __restrict__ pos, int32_t* __restrict__ obs,
+                         const __grid_constant__ CUtensorMap sc_map, int N, int T, int X, int words, int32_t* __restrict__ pos, int32_t* __restrict__ obs,
                          int32_t* __restrict__ reward, uint8_t* __restrict__ done,
                          const int32_t* __restrict__ start, int32_t* __restrict__ env_return,
                          int32_t* __restrict__ env_done, int64_t* stats, uint32_t flags) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   constexpr int kInfoRows = RING::kRows, kInfoStages = RING::kStages, kBulkWarps = RING::kWarps;
   constexpr int EPW = 32 * EPT, ROWB = EPW * 4;
-  constexpr uint32_t kBoxBytes = kInfoRows * ROWB;
+  constexpr uint32_t kActBytes = kInfoRows * ROWB;              // one box of actions
+  constexpr uint32_t kBoxBytes = (SC ? 2 : 1) * kActBytes;       // one ring stage: actions [+ start choices]
+  static_assert(!(SC && PACKED), "start-choice streams are per step: int32 actions only");
   const int lane = threadIdx.x & 31;
   const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);       // warp-uniform for the TMA operands
-  const uint32_t per_warp = (static_cast<uint32_t>(words) + kInfoStages * kInfoRows) * ROWB;
+  const uint32_t per_warp = static_cast<uint32_t>(words) * ROWB + kInfoStages * kBoxBytes;
   const uint32_t tab_s = ((smem_u32(smem_raw) + 127u) & ~127u) + warp * per_warp;   // [words][EPW] words
   const uint32_t act_s = tab_s + static_cast<uint32_t>(words) * ROWB;      // [stages][rows][EPW] words
   __shared__ __align__(8) uint64_t bars[kBulkWarps][kInfoStages + 1];
@@ -158,6 +163,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
       for (int b = 0; b < kInfoStages && b < nbatch; ++b) {
         mbar_expect_tx(bar0 + 8 * b, kBoxBytes);
         tma_load_2d(act_s + b * kBoxBytes, &act_map, env0, b * kInfoRows, bar0 + 8 * b);
+        if (SC) tma_load_2d(act_s + b * kBoxBytes + kActBytes, &sc_map, env0, b * kInfoRows, bar0 + 8 * b);
       }
     }
     int p[EPT], st[EPT];
@@ -166,7 +172,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       p[k] = pos[env0 + k * 32 + lane];
-      st[k] = AUTO_RESET ? start[env0 + k * 32 + lane] : 0;      // lv->start may be NULL without auto-reset
+      st[k] = (AUTO_RESET && !SC) ? start[env0 + k * 32 + lane] : 0;      // lv->start may be NULL otherwise
       fsum[k] = 0;
       fsq[k] = 0;
       tabk[k] = tab_s + (k * 32 + lane) * 4;
@@ -181,10 +187,10 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
       inf[k] = info_at(k, p[k]);
-      inf_st[k] = AUTO_RESET ? info_at(k, st[k]) : 0u;
+      inf_st[k] = (AUTO_RESET && !SC) ? info_at(k, st[k]) : 0u;
     }
 
-    auto step_one = [&](int k, uint32_t a, int t) {
+    auto step_one = [&](int k, uint32_t a, int t, uint32_t sc_addr) {
       const uint32_t allowed = (inf[k] >> a) & 1u;
       // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
       int d, n;
@@ -200,7 +206,10 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
       }
       fsum[k] += f;                               // 64*goals + 128*lavas
       fsq[k] += f * f;                            // 4096*goals + 16384*lavas
-      if (AUTO_RESET && f) { n = st[k]; i2 = inf_st[k]; }
+      if (AUTO_RESET && f) {
+        if (SC) { n = static_cast<int>(lds_u32(sc_addr + k * 128)); i2 = info_at(k, n); }
+        else { n = st[k]; i2 = inf_st[k]; }
+      }
       p[k] = n;
       inf[k] = i2;
     };
@@ -208,7 +217,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
     auto step_row = [&](uint32_t arow, int row, bool full) {   // arow: smem address of this lane's word in the row
       if (!PACKED) {
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) step_one(k, lds_u32(arow + k * 128) & 3u, row);
+        for (int k = 0; k < EPT; ++k) step_one(k, lds_u32(arow + k * 128) & 3u, row, arow + kActBytes);
       } else {
         uint32_t w[EPT];
 #pragma unroll
@@ -217,12 +226,12 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
           for (int s = 0; s < 16; ++s) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s);
+            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s, 0u);
           }
         } else {
           for (int s = 0; row * 16 + s < T; ++s) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s);
+            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s, 0u);
           }
         }
       }
@@ -244,6 +253,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
       if (b + kInfoStages < nbatch && elect_one()) {
         mbar_expect_tx(bar0 + 8 * stage, kBoxBytes);
         tma_load_2d(act_s + stage * kBoxBytes, &act_map, env0, (b + kInfoStages) * kInfoRows, bar0 + 8 * stage);
+        if (SC) tma_load_2d(act_s + stage * kBoxBytes + kActBytes, &sc_map, env0, (b + kInfoStages) * kInfoRows, bar0 + 8 * stage);
       }
       if (++stage == kInfoStages) { stage = 0; parity ^= 1u; }
     }
@@ -293,27 +303,29 @@ static bool make_map_i32(CUtensorMap* map, const void* base, int64_t rows, int64
 }
 
 template <typename RING>
-static size_t info8_smem_bytes(int words, int ept) {
-  return static_cast<size_t>(RING::kWarps) * (static_cast<size_t>(words) + RING::kStages * RING::kRows) * 32 * ept * 4 + 128;
+static size_t info8_smem_bytes(int words, int ept, bool sc = false) {
+  return static_cast<size_t>(RING::kWarps) * (static_cast<size_t>(words) + (sc ? 2 : 1) * RING::kStages * RING::kRows) * 32 * ept * 4 + 128;
 }
 
-template <int EPT, bool TRAJ, bool AR, typename RING, bool PACKED>
+template <int EPT, bool TRAJ, bool AR, typename RING, bool PACKED, bool SC = false>
 static int launch_info8(const gu_levels* lv, int64_t n, int64_t T, const int32_t* actions, int32_t* pos, int32_t* obs,
                         int32_t* reward, uint8_t* done, int32_t* env_return, int32_t* env_done, int64_t* stats,
-                        const uint32_t* tables, uint32_t flags, cudaStream_t st) {
+                        const uint32_t* tables, uint32_t flags, cudaStream_t st, const int32_t* start_choice = nullptr) {
   const int cells = lv->X * lv->Y, words = (cells + 3) / 4;
   constexpr int EPW = 32 * EPT;
   const int64_t act_rows = PACKED ? (T + 15) / 16 : T;
-  CUtensorMap act_map, tab_map;
+  CUtensorMap act_map, tab_map, sc_map;
   if (!make_map_i32(&act_map, actions, act_rows, n, RING::kRows, EPW) ||
       !make_map_i32(&tab_map, tables, words, n, words, EPW))
     return GU_ERR_UNSUPPORTED;
-  const size_t smem = info8_smem_bytes<RING>(words, EPT);
+  sc_map = act_map;
+  if (SC && !make_map_i32(&sc_map, start_choice, T, n, RING::kRows, EPW)) return GU_ERR_UNSUPPORTED;
+  const size_t smem = info8_smem_bytes<RING>(words, EPT, SC);
   const unsigned blocks = static_cast<unsigned>((n / EPW + RING::kWarps - 1) / RING::kWarps);
-  auto kernel = rollout_info8_tma_kernel<EPT, TRAJ, AR, RING, PACKED>;
+  auto kernel = rollout_info8_tma_kernel<EPT, TRAJ, AR, RING, PACKED, SC>;
   cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
   if (e != cudaSuccess) return static_cast<int>(e);
-  kernel<<<blocks, RING::kWarps * 32, smem, st>>>(act_map, tab_map, static_cast<int>(n), static_cast<int>(T), lv->X,
+  kernel<<<blocks, RING::kWarps * 32, smem, st>>>(act_map, tab_map, sc_map, static_cast<int>(n), static_cast<int>(T), lv->X,
                                                  words, pos, obs, reward, done, lv->start, env_return, env_done, stats,
                                                  flags);
   cudaError_t le = cudaGetLastError();
@@ -407,8 +419,9 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
   const bool traj = obs || reward || done;
   const bool packed = flags & GU_FLAG_PACKED_ACTIONS;
   if (fmt == kTableINFO8) {
-    if (start_choice != nullptr || !al16(actions) || !al16(tables) || n % 32 != 0 || n >= (1ll << 31))
-      return GU_ERR_UNSUPPORTED;
+    if (!al16(actions) || !al16(tables) || n % 32 != 0 || n >= (1ll << 31)) return GU_ERR_UNSUPPORTED;
+    const bool sc = start_choice != nullptr && (flags & GU_FLAG_AUTO_RESET);
+    if (sc && (packed || !al16(start_choice))) return GU_ERR_UNSUPPORTED;   // per-step stream: int32 actions only
     // envs per lane: 2 when that still gives every SM a dozen warps (measured best on B200 for large
     // batches), else 1 so small batches spread over all SMs; 4 only on request
     static const char* force = getenv("GU_INFO8_EPT");
@@ -433,6 +446,15 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
       GU_INFO8_P(EPT, RING, false);    \
     }                                  \
   } while (0)
+    if (sc) {      // multi-start levels: the start-choice stream rides the ring behind the actions
+#define GU_INFO8_SC(EPT)                                                                                      \
+  return traj ? launch_info8<EPT, true, true, RingStd, false, true>(GU_INFO8_ARGS, start_choice)              \
+              : launch_info8<EPT, false, true, RingStd, false, true>(GU_INFO8_ARGS, start_choice)
+      if (ept == 4) GU_INFO8_SC(4);
+      if (ept == 2) GU_INFO8_SC(2);
+      GU_INFO8_SC(1);
+#undef GU_INFO8_SC
+    }
     if (ept == 4) GU_INFO8(4, RingStd);
     if (ept == 2) GU_INFO8(2, RingStd);
     if (deep) GU_INFO8(1, RingDeep);

@@ -75,6 +75,35 @@ def test_packed_actions_equal_int32_actions(shape, n, T, per_env, tables, auto_r
         assert r2["h2d_bytes"] * 16 == r1["h2d_bytes"]
 
 
+@pytest.mark.parametrize("shape,n,T", [((8, 8), 4096, 90), ((8, 8), 131072, 40), ((16, 16), 1024, 200)])
+def test_start_choice_stream_on_the_table_kernels(shape, n, T):
+    """Multi-start levels (several 'x' cells: reset draws random.choice, griduniverse_env.py:189): the
+    host-supplied start-choice stream rides the TMA ring; trajectories equal the oracle's."""
+    X, Y = shape
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, seed=6)
+    rs = np.random.RandomState(8)
+    actions = rs.randint(0, 4, (T, n)).astype(np.int32)
+    # a second start candidate per env: any open non-terminal cell; the stream picks one of the two per (t, env)
+    open_cells = ~(wall | goal | lava)
+    alt = np.array([np.flatnonzero(open_cells[i])[rs.randint(open_cells[i].sum())] for i in range(min(n, 2048))])
+    alt = np.resize(alt, n).astype(np.int32)
+    alt = np.where(open_cells[np.arange(n), alt], alt, start).astype(np.int32)
+    sc = np.where(rs.randint(0, 2, (T, n)) == 1, alt[None, :], start[None, :]).astype(np.int32)
+    lv = synth.env_levels_device(X, Y, n, seed=6)
+    env = GridUniverseVecEnv(n, levels=lv, auto_reset=True)
+    assert env.levels.tables is not None
+    out = env.rollout(torch.from_numpy(actions).cuda(), trajectories=True, start_choice=torch.from_numpy(sc).cuda())
+    env2 = GridUniverseVecEnv(n, levels=lv, auto_reset=True, use_tables=False)
+    ref = env2.rollout(torch.from_numpy(actions).cuda(), trajectories=True, start_choice=torch.from_numpy(sc).cuda())
+    for k in ("obs", "reward", "done", "pos", "env_return", "env_done", "stats"):
+        assert torch.equal(out[k], ref[k]), k
+    m = 512                                              # a subset through the oracle
+    olevels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(m)]
+    eo, er, ed, ep = orc.rollout(olevels, start[:m], actions[:, :m], auto_reset=True, start_choice=sc[:, :m])
+    assert np.array_equal(out["obs"][:, :m].cpu().numpy(), eo) and np.array_equal(out["pos"][:m].cpu().numpy(), ep)
+    assert np.array_equal(out["reward"][:, :m].cpu().numpy(), er)
+
+
 def test_large_batch_vs_oracle():
     """A batch just below the two-envs-per-lane threshold (one env per lane, many waves of warps),
     every env replayed through the oracle."""
