@@ -101,39 +101,42 @@ class Level(object):
 
 
 def read_level_file(fp):
-    """griduniverse_env.py:246-251: rstrip lines, drop empty ones, remove all whitespace."""
+    """A level file as the list of its non-blank rows with every whitespace character removed
+    (what griduniverse_env.py:246-251 feeds the text parser)."""
     with open(fp, 'r') as f:
-        all_lines = [line.rstrip() for line in f.readlines()]
-    return ["".join(line.split()) for line in all_lines if line]
+        rows = ("".join(raw.split()) for raw in f)
+        return [row for row in rows if row]
 
 
-def parse_level_text(text_world_lines):
-    """griduniverse_env.py:253-300: 'o' floor, '#' wall, 'G' goal, 'L' lava, 'x' start."""
-    goals, starts, lavas, walls = [], [], [], []
-    curr_index = 0
-    width_of_grid = len(text_world_lines[0])
-    for line in text_world_lines:
-        if len(line) != width_of_grid:
-            raise ValueError("Input text file is not a rectangle")
-        for char in line:
-            if char == 'G':
-                goals.append(curr_index)
-            elif char == 'L':
-                lavas.append(curr_index)
-            elif char == 'o':
-                pass
-            elif char == '#':
-                walls.append(curr_index)
-            elif char == 'x':
-                starts.append(curr_index)
-            else:
-                raise ValueError('Invalid Character "{}". Returning'.format(char))
-            curr_index += 1
-    if len(starts) == 0:
+# cell classes of the level alphabet (griduniverse_env.py:282-291); anything else is invalid
+_FLOOR, _WALL, _GOAL, _LAVA, _START, _INVALID = 0, 1, 2, 3, 4, 255
+_CELL_CLASS = np.full(256, _INVALID, dtype=np.uint8)
+for _ch, _cls in (("o", _FLOOR), ("#", _WALL), ("G", _GOAL), ("L", _LAVA), ("x", _START)):
+    _CELL_CLASS[ord(_ch)] = _cls
+
+
+def parse_level_text(rows):
+    """Rows of 'o' floor / '#' wall / 'G' goal / 'L' lava / 'x' start -> Level, with the reference's
+    ValueErrors in the order its row-major scan meets them (griduniverse_env.py:253-300): an invalid
+    character in an earlier row wins over a ragged later row; missing 'x' / 'G' are reported after the
+    scan.  The whole grid is classified with one byte look-up table instead of a per-character loop
+    (a 16384 x 16384 level is 268 M characters)."""
+    X = len(rows[0])
+    ragged = next((i for i, row in enumerate(rows) if len(row) != X), None)
+    scanned = rows if ragged is None else rows[:ragged]
+    text = "".join(scanned)
+    cls = _CELL_CLASS[np.frombuffer(text.encode("latin-1", "replace"), dtype=np.uint8)]
+    bad = np.flatnonzero(cls == _INVALID)
+    if bad.size:
+        raise ValueError('Invalid Character "{}". Returning'.format(text[int(bad[0])]))
+    if ragged is not None:
+        raise ValueError("Input text file is not a rectangle")
+    cells = {c: np.flatnonzero(cls == c).tolist() for c in (_WALL, _GOAL, _LAVA, _START)}
+    if not cells[_START]:
         raise ValueError("No starting states set in text file. Place \"x\" within grid. ")
-    if len(goals) == 0:
+    if not cells[_GOAL]:
         raise ValueError("No terminal goal states set in text file. Place \"T\" within grid. ")
-    return Level(width_of_grid, len(text_world_lines), walls=walls, goals=goals, lavas=lavas, starts=starts)
+    return Level(X, len(rows), walls=cells[_WALL], goals=cells[_GOAL], lavas=cells[_LAVA], starts=cells[_START])
 
 
 # --------------------------------------------------------------------------

@@ -53,6 +53,14 @@ def test_level_text_parser(golden_levels, tmp_path):
         assert np.array_equal(lv.lava, olv.lava) and lv.starting_states == olv.starts
         assert np.array_equal(lv.rewards(), olv.reward)
         assert lv.to_text_lines() == orc.strip_level_lines(lines)
+    # error order of the row-major scan (griduniverse_env.py:277-293): whichever comes first in the text
+    for rows in (["xo?", "oG"], ["xoo", "oG", "o?o"], ["xoo", "ooo"], ["ooG", "ooo"], ["xoG", "o\u00e9o"]):
+        msgs = []
+        for parse in (parse_level_text, orc.parse_level_text):
+            with pytest.raises(ValueError) as e:
+                parse(rows)
+            msgs.append(str(e.value))
+        assert msgs[0] == msgs[1]
     # file path + whitespace / blank-line stripping (griduniverse_env.py:246-251)
     fp = tmp_path / "lvl.txt"
     fp.write_text("x o #\n\n o o G \n")
