@@ -15,6 +15,8 @@
 //
 // Per-cell static data comes from the derived `info` plane (gu_pack_info): one bit per action
 // "a is blocked" (grid edge | wall at the target | s terminal) plus the goal and lava bits.
+#include <cuda.h>
+
 #include <cstdlib>
 
 #include "gu_cell.cuh"
@@ -408,18 +410,54 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
 #ifndef GU_TILED_MIN_BLOCKS
 #define GU_TILED_MIN_BLOCKS 3
 #endif
+#ifndef GU_TILED_MIN_BLOCKS_F64
+#define GU_TILED_MIN_BLOCKS_F64 3
+#endif
 template <typename T, int KIND, bool WRITE_TIE>
 constexpr int tiled_min_blocks() {
-  return sizeof(T) != 4 ? 1 : ((KIND == GU_POLICY_GREEDY && !WRITE_TIE) ? GU_TILED_MIN_BLOCKS : 4);
+  return sizeof(T) != 4 ? GU_TILED_MIN_BLOCKS_F64 : ((KIND == GU_POLICY_GREEDY && !WRITE_TIE) ? GU_TILED_MIN_BLOCKS : 4);
 }
-template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false>
+// ---- TMA-staged window (TMA = true) ------------------------------------------------------------------
+// Each warp's strip of the value grid and of the info plane arrives as 2-D TMA tiles
+// (cp.async.bulk.tensor.2d, SASS UTMALDG) of kTmaRows rows -- the strip plus one 16-byte unit of halo on
+// either side, out-of-range columns zero-filled by the hardware -- through a kTmaStages-deep ring in
+// shared memory, completed on per-warp mbarriers; no block-level barrier in the row loop.  The window
+// rows are then read with shared loads, so there are no global loads, no L2 prefetches and no halo-column
+// special case in the loop, and several KB per warp are always in flight.
+// Tensor maps: the value array is described as 8-byte elements (two f32 / one f64) and the info plane as
+// 4-byte elements, which keeps the 264-column boxes under the 256-element box limit.
+#ifndef GU_TMA_ROWS
+#define GU_TMA_ROWS 4
+#endif
+#ifndef GU_TMA_STAGES
+#define GU_TMA_STAGES 3
+#endif
+constexpr int kTmaRows = GU_TMA_ROWS, kTmaStages = GU_TMA_STAGES;
+template <typename T>
+struct TmaGeom {
+  static constexpr int CPT = Vec<T>::W * 2;                                  // cells per thread (NV = 2)
+  static constexpr int kPadV = 16 / static_cast<int>(sizeof(T));             // halo unit of V, elements
+  static constexpr int kVRowBytes = (32 * CPT + 2 * kPadV) * static_cast<int>(sizeof(T));
+  static constexpr int kIRowBytes = 32 * CPT + 32;                           // info: 16 bytes of halo each side
+  static constexpr int kStageBytes = kTmaRows * (kVRowBytes + kIRowBytes);
+  static constexpr int kWarpBytes = kTmaStages * kStageBytes;
+  static_assert((kTmaRows * kVRowBytes) % 128 == 0 && kStageBytes % 128 == 0, "TMA destinations are 128-byte aligned");
+};
+
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* map, int x, int y, uint32_t bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(map), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+
+template <typename T, int KIND, bool WRITE_TIE, int NV, bool PEER = false, bool TMA = false>
 __global__ void __launch_bounds__(kTiledWarps * 32, (tiled_min_blocks<T, KIND, WRITE_TIE>()))
 sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __restrict__ vin,
                    T* __restrict__ vout, uint8_t* __restrict__ tie_out, const void* __restrict__ policy,
                    T gamma, T* residual, const T* gate, T gate_thr, int rows_per_block,
-                   const __grid_constant__ PeerArgs<T> peer) {   // read in place from the constant bank: the
+                   const __grid_constant__ PeerArgs<T> peer,     // read in place from the constant bank: the
                                                                  // helpers take it by reference, and a by-value
                                                                  // copy would be spilled to local memory by every thread
+                   const __grid_constant__ CUtensorMap vmap, const __grid_constant__ CUtensorMap imap) {
   using N = Num<T>;
   using V = typename Vec<T>::type;
   constexpr int W = Vec<T>::W;
@@ -520,7 +558,93 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const int pf_pitch = lane < kVLines ? pitch * static_cast<int>(sizeof(T)) : pitch;   // bytes; prefetch only
   const bool pf_on = pf_base != nullptr && wx0 + (lane < kVLines ? lane * (128 / static_cast<int>(sizeof(T))) : (lane - kVLines) * 128) < g.pitch;
 
+  // ---- TMA ring (TMA = true): per-warp state -------------------------------------------------------
+  extern __shared__ __align__(1024) uint8_t ring_raw[];
+  __shared__ __align__(8) uint64_t ring_bars[TMA ? kTiledWarps : 1][kTmaStages];
+  using TG = TmaGeom<T>;
+  const int warp_u = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);            // warp-uniform for the TMA operands
+  const uint32_t ring_s = TMA ? ((smem_u32(ring_raw) + 127u) & ~127u) + warp_u * TG::kWarpBytes : 0u;
+  const uint32_t bar_s = smem_u32(&ring_bars[TMA ? warp_u : 0][0]);
+  int ld_slot = 0, ld_row = 0, ld_box = 0;      // next row to read: ring slot, row inside its box, box number
+  int cv_row = 0, cv_box = 0;                   // next row to be converted (its box is released after its last row)
+  const int nboxes = TMA ? (ry1 - ry0 + 3 + kTmaRows - 1) / kTmaRows : 0;      // array rows ry0 .. ry1 + 2
+  auto ring_issue = [&](int box) {              // one elected lane: V tile + info tile of box `box`
+    const int slot = box % kTmaStages;
+    const uint32_t dst = ring_s + slot * TG::kStageBytes, bar = bar_s + 8 * slot;
+    mbar_expect_tx(bar, TG::kStageBytes);
+    // x in map elements: V is mapped as 8-byte elements, the info plane as 4-byte elements
+    tma_tile_2d(dst, &vmap, (wx0 - TG::kPadV) * static_cast<int>(sizeof(T)) / 8, ry0 + box * kTmaRows, bar);
+    tma_tile_2d(dst + kTmaRows * TG::kVRowBytes, &imap, (wx0 - 16) / 4, ry0 + box * kTmaRows, bar);
+  };
+  if constexpr (TMA) {
+    if (elect_one()) {
+      for (int i = 0; i < kTmaStages; ++i) mbar_init(bar_s + 8 * i, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+    if (elect_one())
+      for (int b = 0; b < kTmaStages && b < nboxes; ++b) ring_issue(b);
+  }
+  // the row just converted was read from the ring a row earlier: when it was the last row of its box,
+  // every lane is done with that box and its slot takes the box kTmaStages further on
+  auto ring_release = [&]() {
+    if constexpr (TMA) {
+      if (++cv_row == kTmaRows) {
+        cv_row = 0;
+        __syncwarp();
+        if (cv_box + kTmaStages < nboxes && elect_one()) ring_issue(cv_box + kTmaStages);
+        ++cv_box;
+      }
+    }
+  };
+
   auto issue_loads = [&](int ar, WinRow<T, CPT, TIES>& r) {
+    if constexpr (TMA) {
+      // rows are read strictly in order; `ar` is only what the LDG path needs
+      if (ld_row == 0) mbar_wait(bar_s + 8 * ld_slot, static_cast<uint32_t>(ld_box / kTmaStages) & 1u);
+      const uint32_t vrow = ring_s + ld_slot * TG::kStageBytes + ld_row * TG::kVRowBytes;
+      const uint32_t irow = ring_s + ld_slot * TG::kStageBytes + kTmaRows * TG::kVRowBytes + ld_row * TG::kIRowBytes;
+      const uint32_t vme = vrow + (TG::kPadV + lane * CPT) * static_cast<int>(sizeof(T));
+      const uint32_t ime = irow + 16 + lane * CPT;
+#pragma unroll
+      for (int k = 0; k < NV; ++k) {
+        V vec;
+        if constexpr (sizeof(T) == 4)
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(vec.x), "=f"(vec.y), "=f"(vec.z), "=f"(vec.w) : "r"(vme + 16 * k));
+        else
+          asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(vec.x), "=d"(vec.y) : "r"(vme + 16 * k));
+        unpack(vec, r.v + k * W);
+      }
+      if constexpr (CPT == 8) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r.info[0]), "=r"(r.info[1]) : "r"(ime));
+      } else {
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r.info[0]) : "r"(ime));
+      }
+      // halo columns: the unit left of the strip ends with column wx0 - 1, the unit right of it starts
+      // with column wx0 + 32 * CPT (zero-filled outside the array; outside the GRID they are not used)
+      r.hv = T(0);
+      r.hinfo = 0;
+      if (has_l || has_r) {
+        const uint32_t hva = has_l ? vrow + (TG::kPadV - 1) * static_cast<int>(sizeof(T)) : vrow + (TG::kPadV + 32 * CPT) * static_cast<int>(sizeof(T));
+        const uint32_t hia = has_l ? irow + 15 : irow + 16 + 32 * CPT;
+        if constexpr (sizeof(T) == 4) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(r.hv) : "r"(hva));
+        else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(r.hv) : "r"(hva));
+        asm volatile("ld.shared.u8 %0, [%1];" : "=r"(r.hinfo) : "r"(hia));
+      }
+      if (!active) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) r.v[j] = T(0);
+#pragma unroll
+        for (int k = 0; k < IW; ++k) r.info[k] = 0;
+      }
+      if (++ld_row == kTmaRows) {
+        ld_row = 0;
+        ++ld_box;
+        if (++ld_slot == kTmaStages) ld_slot = 0;
+      }
+      return;
+    }
     const int o = ar * pitch + x0;
     if (pf_on) {
       const int par = min(ar + kPrefetchRows, rows + 1);
@@ -628,7 +752,9 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   issue_loads(ry0 + 1, w[1]);                   // array row ry0 + 1 = first owned row
   issue_loads(ry0 + 2, w[2]);
   convert(w[0]);
+  ring_release();
   convert(w[1]);
+  ring_release();
 
   for (int base = ry0; base < ry1; base += 3) {
 #pragma unroll
@@ -639,6 +765,7 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
         WinRow<T, CPT, TIES>& cur = w[(j + 1) % 3];
         WinRow<T, CPT, TIES>& dn = w[(j + 2) % 3];
         convert(dn);                               // row ry + 2, loaded during the previous row
+        ring_release();
         // the row after that goes into the raw fields of `up` (its v / info are dead, its g / rt
         // stay valid for this row's compute); the loads are in flight while this row is computed
         issue_loads(min(ry + 3, last_ar), up);
@@ -927,6 +1054,58 @@ static int choose_rows_per_block(K kernel, int rows, int blocks_x) {
   return def;
 }
 
+// ---- tensor maps of the TMA-staged window ---------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn sweep_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+// 2-D map of a row-major array of `elem`-byte map elements: cols x rows, rows row_bytes apart
+static bool sweep_map(CUtensorMap* map, CUtensorMapDataType dt, const void* base, uint64_t cols, uint64_t rows,
+                      uint64_t row_bytes, uint32_t box_cols, uint32_t box_rows) {
+  EncodeTiledFn fn = sweep_encode_fn();
+  if (!fn) return false;
+  const cuuint64_t dims[2] = {cols, rows};
+  const cuuint64_t strides[1] = {row_bytes};
+  const cuuint32_t box[2] = {box_cols, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  return fn(map, dt, 2, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+// Which window feeds a sweep: TMA tiles through the shared-memory ring, or 16-byte global loads one row
+// ahead + L2 prefetch three rows ahead.  Measured on B200 at 16384^2 (ms per sweep, LDG / TMA):
+//   f32  fused-greedy 0.482 / 0.499   tie-mask 0.528 / 0.547   uniform 0.393 / 0.387   extraction 0.453 / 0.464
+//   f64  fused-greedy 1.269 / 1.192   tie-mask 1.033 / 1.057   uniform 0.707 / 0.715   extraction 0.738 / 0.699
+// The fp32 kernels are bound by instruction issue and the ALU pipe, not by the mover, and the ring's
+// 65 KB per block costs the tie-mask kernels a resident block; the fp64 fused-greedy sweep and
+// extraction (8 warps of 164+ registers per SM, little latency hiding of their own) gain 6 %.
+// Default: TMA where it wins.  GU_SWEEP_TMA=1 / 0 forces one path everywhere (both are bit-identical).
+static bool sweep_tma_enabled(size_t elem, int kind, bool write_tie) {
+  static const char* e = getenv("GU_SWEEP_TMA");
+  if (e && (e[0] == '0' || e[0] == '1')) return e[0] == '1';
+  return elem == 8 && (write_tie || kind == GU_POLICY_GREEDY);
+}
+template <typename T>
+static bool make_sweep_maps(const gu_grid* g, const T* vin, CUtensorMap* vmap, CUtensorMap* imap) {
+  using TG = TmaGeom<T>;
+  const uint64_t arows = static_cast<uint64_t>(g->row_end - g->row_begin + 2);
+  const uint64_t pitch = static_cast<uint64_t>(g->pitch);
+  return sweep_map(vmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, vin, pitch * sizeof(T) / 8, arows, pitch * sizeof(T),
+                   TG::kVRowBytes / 8, kTmaRows) &&
+         sweep_map(imap, CU_TENSOR_MAP_DATA_TYPE_UINT32, g->info, pitch / 4, arows, pitch, TG::kIRowBytes / 4, kTmaRows);
+}
+template <typename T>
+static size_t sweep_ring_bytes() { return static_cast<size_t>(kTiledWarps) * TmaGeom<T>::kWarpBytes + 128; }
+
 template <typename T>
 static int make_peer_args(const gu_peer_links* pl, PeerArgs<T>* out) {
   if (!pl || !pl->done_counter || !pl->error_flag || !pl->halo_flags || !pl->edge_counters || !pl->stop_flag)
@@ -966,11 +1145,16 @@ static bool sweep_pdl_enabled() {
   return e && e[0] == '1';
 }
 template <typename... KArgs, typename... Args>
-static cudaError_t launch_sweep(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t st, Args... args) {
+static cudaError_t launch_sweep(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                Args... args) {
+  if (smem > 0) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    if (e != cudaSuccess) return e;
+  }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = block;
-  cfg.dynamicSmemBytes = 0;
+  cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
@@ -996,9 +1180,17 @@ static int launch_tiled_peer(const gu_grid* g, const T* vin, T* vout, int kind, 
   dim3 grid(bx, (rows + rpb - 1) / rpb);
   if (grid.y > 65535u) return GU_ERR_SHAPE;
   const GridView v = tview(g);
-#define GU_LAUNCH_PEER(KIND)                                                                                    \
-  launch_sweep(sweep_tiled_kernel<T, KIND, false, NV, true>, grid, dim3(kTiledWarps * 32), st, v, g->info, vin, \
-               vout, static_cast<uint8_t*>(nullptr), policy, gamma, residual, static_cast<const T*>(nullptr), T(0), rpb, pa)
+  CUtensorMap vmap = {}, imap = {};
+  const bool tma = NV == 2 && sweep_tma_enabled(sizeof(T), kind, false) && make_sweep_maps<T>(g, vin, &vmap, &imap);
+#define GU_LAUNCH_PEER_T(KIND, TMA)                                                                                   \
+  launch_sweep(sweep_tiled_kernel<T, KIND, false, NV, true, TMA>, grid, dim3(kTiledWarps * 32),                       \
+               TMA ? sweep_ring_bytes<T>() : 0, st, v, g->info, vin, vout, static_cast<uint8_t*>(nullptr), policy, gamma, \
+               residual, static_cast<const T*>(nullptr), T(0), rpb, pa, vmap, imap)
+#define GU_LAUNCH_PEER(KIND)          \
+  do {                                \
+    if (tma) GU_LAUNCH_PEER_T(KIND, true); \
+    else GU_LAUNCH_PEER_T(KIND, false);    \
+  } while (0)
   switch (kind) {
     case GU_POLICY_PROBS: GU_LAUNCH_PEER(GU_POLICY_PROBS); break;
     case GU_POLICY_MASK: GU_LAUNCH_PEER(GU_POLICY_MASK); break;
@@ -1007,6 +1199,7 @@ static int launch_tiled_peer(const gu_grid* g, const T* vin, T* vout, int kind, 
     default: return GU_ERR_MODE;
   }
 #undef GU_LAUNCH_PEER
+#undef GU_LAUNCH_PEER_T
   GU_CHECK_LAUNCH();
   return GU_OK;
 }
@@ -1024,9 +1217,17 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
   if (grid.y > 65535u) return GU_ERR_SHAPE;
   const GridView v = tview(g);
   const uint8_t* info = g->info;
-#define GU_LAUNCH(KIND)                                                                                        \
-  launch_sweep(sweep_tiled_kernel<T, KIND, WRITE_TIE, NV, false>, grid, dim3(kTiledWarps * 32), st, v, info, vin, vout, \
-               tie, policy, gamma, residual, gate, gate_thr, rpb, PeerArgs<T>())
+  CUtensorMap vmap = {}, imap = {};
+  const bool tma = NV == 2 && sweep_tma_enabled(sizeof(T), kind, WRITE_TIE) && make_sweep_maps<T>(g, vin, &vmap, &imap);
+#define GU_LAUNCH_T(KIND, TMA)                                                                                      \
+  launch_sweep(sweep_tiled_kernel<T, KIND, WRITE_TIE, NV, false, TMA>, grid, dim3(kTiledWarps * 32),                \
+               TMA ? sweep_ring_bytes<T>() : 0, st, v, info, vin, vout, tie, policy, gamma, residual, gate, gate_thr, rpb, \
+               PeerArgs<T>(), vmap, imap)
+#define GU_LAUNCH(KIND)               \
+  do {                                \
+    if (tma) GU_LAUNCH_T(KIND, true); \
+    else GU_LAUNCH_T(KIND, false);    \
+  } while (0)
   if (WRITE_TIE) {
     GU_LAUNCH(GU_POLICY_GREEDY);
   } else {
@@ -1039,6 +1240,7 @@ static int launch_tiled(const gu_grid* g, const T* vin, T* vout, uint8_t* tie, i
     }
   }
 #undef GU_LAUNCH
+#undef GU_LAUNCH_T
   GU_CHECK_LAUNCH();
   return GU_OK;
 }

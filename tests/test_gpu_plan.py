@@ -174,3 +174,20 @@ def test_monte_carlo_evaluation_matches_reference(golden, golden_levels, golden_
         st, rw, done = monte_carlo.run_episode(pol, env)
         assert st == list(golden["mc/%s/ep%d/states" % (variant, i)])
         assert rw == list(golden["mc/%s/ep%d/rewards" % (variant, i)])
+
+
+@pytest.mark.parametrize("tma", ["0", "1"])
+def test_both_window_paths_are_bit_exact(tma):
+    """The sweep kernels have two data paths for the value window (2-D TMA tiles through a shared-memory
+    ring / 16-byte global loads + L2 prefetch), chosen per kernel by measurement; GU_SWEEP_TMA forces one
+    everywhere.  Both must reproduce the oracle bit for bit (the switch is read once per process, hence
+    the child interpreter)."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, GU_SWEEP_TMA=tma)
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", os.path.join(root, "tests", "test_gpu_plan.py"),
+                        "-k", "synthetic_maze_vs_oracle or single_sweep_and_greedy_golden or gate_freezes"],
+                       env=env, cwd=root, capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]

@@ -39,7 +39,7 @@ def main():
             out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "quick_perf.py"), "sweep"], env=env,
                                  capture_output=True, text=True).stdout
             print(lib)
-            print("\n".join(l for l in out.splitlines() if "greedy " in l or "uniform" in l))
+            print("\n".join(l for l in out.splitlines() if "greedy" in l or "uniform" in l or "mask" in l))
 
 
 if __name__ == "__main__":
