@@ -318,6 +318,7 @@ class PeerValueIteration(ShardedValueIteration):
             timeout_s = float(os.environ.get("GU_PEER_TIMEOUT_S", "3"))
         self.timeout_cycles = int(timeout_s * 1.9e9)
         self._graphs = {}
+        self.inflight = 2                       # chunks of sweeps enqueued ahead of the host's reads
         self._alloc()
         self.exchange_halos(self._bufs[0])     # sets up NCCL's point-to-point channels outside any timed solve
 
@@ -478,7 +479,7 @@ class PeerValueIteration(ShardedValueIteration):
         thr = pl.np_dtype.type(threshold)
         chunk = max(2, int(chunk) + (int(chunk) & 1))
         s0 = self._next_slot
-        assert s0 + budget <= self.max_slots, "raise max_slots"
+        assert s0 + budget + 2 <= self.max_slots, "raise max_slots"
         cur0 = self._cur
         self._zero_stop()                                  # sticky stop word of the previous phase
         if use_graph and getattr(self, "_graph_res", None) is None:
@@ -488,7 +489,7 @@ class PeerValueIteration(ShardedValueIteration):
         pending = []                                       # (event, snapshot index, sweeps enqueued so far)
         snap = 0
         while not converged and evald < budget:
-            while len(pending) < 2 and enq < budget:       # keep two chunks in flight
+            while len(pending) < self.inflight and enq < budget:       # keep two chunks in flight
                 n = min(chunk, budget - enq)
                 graph = None
                 if use_graph and s0 == 0 and enq > 0 and n == chunk == self._graph_res.numel():
@@ -525,7 +526,12 @@ class PeerValueIteration(ShardedValueIteration):
                 if row.max() < thr:
                     converged = True
                     break
-        self._next_slot = s0 + enq
+        # Slots the next phase may use.  This must be the SAME number on every rank (slot indices name
+        # table rows and halo-flag values across ranks), so it cannot depend on how many chunks this
+        # rank's host happened to have enqueued: after convergence at sweep evald - 1 exactly two more
+        # sweeps touched the protocol state on every rank -- the lag sweep and the one that set the stop
+        # word; everything after them was a no-op that never published.
+        self._next_slot = s0 + (evald + 2 if converged else max(enq, evald))
         self._last_slot = s0 + evald - 1
         self._cur = (cur0 + evald) % 2
         return evald, last, converged

@@ -126,9 +126,12 @@ class EmulatedPeerDriver(PeerValueIteration):
         self.exchange_halos(self._bufs[src])      # = the neighbours' stores of the sweep before
         res = torch.full((1,), float("-inf"), dtype=torch.float64)
         self.pl.sweep(self._bufs[src], self._bufs[1 - src], kind, pol_t, gamma, res)
-        rows = [torch.empty(1, dtype=torch.float64) for _ in range(self.world)]
-        dist.all_gather(rows, res)
-        self._table[slot] = torch.cat(rows)
+        # the real kernels write into the OTHER ranks' tables and flag words at this slot index, so a sweep
+        # must carry the same slot number on every rank
+        rows = [torch.empty(2, dtype=torch.float64) for _ in range(self.world)]
+        dist.all_gather(rows, torch.cat([res, torch.tensor([float(slot)], dtype=torch.float64)]))
+        assert all(int(r[1]) == slot for r in rows), "ranks disagree on the slot number of a sweep"
+        self._table[slot] = torch.stack([r[0] for r in rows])
         self.ran += 1
 
     def _peer_wait(self, slot):
@@ -165,6 +168,8 @@ def _worker(rank, world, port, X, Y, chunk, out_dir, driver, algo, max_steps):
         r0, r1 = shard_rows(Y, world, rank)
         pl = OraclePlanner(wall, goal, lava, X, Y, r0, r1)
         svi = EmulatedPeerDriver(pl) if driver == "peer" else ShardedValueIteration(pl)
+        if driver == "peer":
+            svi.inflight = 2 + rank % 2       # hosts run ahead by different amounts: slot numbering must not care
         exhausted = False
         for _ in range(2 if driver == "peer" else 1):      # peer: a second solve on the same driver (reset path)
             pl.sweeps_run = 0
