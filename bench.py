@@ -329,10 +329,11 @@ def run_ours(args):
         dist.all_reduce(ok, op=dist.ReduceOp.MIN)      # every rank must take the same path
         if ok.item() == 0:
             svi, vi_comm = ShardedValueIteration(pl), "nccl send/recv + all-reduce per sweep (fallback)"
+    vi_chunk = 16 if world <= 2 else 8      # sweeps per host read: after convergence up to two chunks of no-op launches drain
     vi_meta = {}
 
     def vi_pass():
-        v, tie, sweeps, last = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=16)
+        v, tie, sweeps, last = svi.value_iteration("uniform", None, VI_THETA, 1000, VI_GAMMA, chunk=vi_chunk)
         vi_meta["sweeps"], vi_meta["last"] = sweeps, last
 
     vi_pass()                                          # warm-up solve (also fixes the sweep count)
@@ -361,7 +362,7 @@ def run_ours(args):
 
     def vi_e2e_pass():
         s, last, h2d, d2h = svi.solve_host(v0_h, v_h, tie_h, "uniform", threshold=VI_THETA, max_steps=1000,
-                                           discount_factor=VI_GAMMA, chunk=16)
+                                           discount_factor=VI_GAMMA, chunk=vi_chunk)
         io["h2d"], io["d2h"], io["sweeps"] = h2d, d2h, s
 
     vi_e2e_pass()
@@ -377,7 +378,7 @@ def run_ours(args):
     pi_meta = {}
 
     def pi_pass():
-        v, tie, n, d_eval, exhausted = svi.policy_iteration("uniform", None, VI_THETA, PI_STEPS, VI_GAMMA, chunk=16)
+        v, tie, n, d_eval, exhausted = svi.policy_iteration("uniform", None, VI_THETA, PI_STEPS, VI_GAMMA, chunk=vi_chunk)
         pi_meta.update(sweeps=n, delta_eval=d_eval, exhausted=bool(exhausted), v=v, tie=tie)
 
     pi_pass()
@@ -657,8 +658,19 @@ def run_profile(args):
     actions = torch.randint(0, 4, (ENV_T, n), dtype=torch.int32, device=dev)
     for _ in range(2):
         env.rollout(actions, trajectories=False, per_env=True)
+    packed, _ = env.pack_actions(actions)
+    env.rollout(packed, trajectories=False, per_env=True, packed_steps=ENV_T)
     env.step(actions[0])
-    del actions
+    del actions, packed
+    # cfg 2 in batch form: 4,736 10x10 mazes, one block each
+    from griduniverse_b200.batch import MazeBatch
+    from griduniverse_b200.envs import GridUniverseEnv
+    with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:
+        lv10 = json.load(f)
+    base = [GridUniverseEnv.from_text_lines(lv10["gen10_%d" % k]).level for k in range(10)]
+    mb = MazeBatch([base[i % 10] for i in range(148 * 32)], device=dev)
+    mb.value_iteration("uniform", None, 1e-6, 1000, 0.9)
+    mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9)
     size = VI_SIZE // max(1, int(args.profile_div ** 0.5) // 2 * 2 or 1)
     for dt in (np.float32, np.float64):
         grid = synth.maze_plan_grid(size, size, seed=0, dtype=dt, device=dev)

@@ -537,11 +537,11 @@ class PeerValueIteration(ShardedValueIteration):
         return evald, last, converged
 
     def value_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                        discount_factor=1.0, chunk=16, use_graph=True):
+                        discount_factor=1.0, chunk=8, use_graph=True):
         return ShardedValueIteration.value_iteration(self, policy, value_function, threshold, max_steps,
                                                      discount_factor, chunk, use_graph)
 
     def policy_iteration(self, policy="uniform", value_function=None, threshold=1e-5, max_steps=1000,
-                         discount_factor=1.0, chunk=16, use_graph=True):
+                         discount_factor=1.0, chunk=8, use_graph=True):
         return ShardedValueIteration.policy_iteration(self, policy, value_function, threshold, max_steps,
                                                       discount_factor, chunk, use_graph)
