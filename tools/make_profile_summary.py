@@ -46,9 +46,9 @@ with open(os.path.join(ROOT, "profiles", tag + "_ncu_summary.txt"), "w") as f:
             f.write("  %-80s %s %s\n" % (w, r[i], units[i]))
         rd = gb(r[hdr.index("dram__bytes_read.sum")], units[hdr.index("dram__bytes_read.sum")])
         wr = gb(r[hdr.index("dram__bytes_write.sum")], units[hdr.index("dram__bytes_write.sum")])
-        if "rollout_info8_tma_kernel<2, 0, 1, gu::RingStd, 0" in r[ik]:
+        if "rollout_info8_tma_kernel<2, 0, 1, RingStd, 0" in r[ik]:
             traffic["rollout_cfg4"] = rd + wr
-        if "rollout_info8_tma_kernel<2, 0, 1, gu::RingStd, 1" in r[ik]:
+        if "rollout_info8_tma_kernel<2, 0, 1, RingStd, 1" in r[ik]:
             traffic["rollout_cfg4_packed"] = rd + wr
         if "sweep_tiled_kernel<float, 3, 0" in r[ik]:
             traffic["sweep_greedy_f32_cfg5"] = rd + wr
