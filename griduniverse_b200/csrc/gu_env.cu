@@ -10,11 +10,25 @@ namespace gu {
 
 // ---- one step per launch ("gym mode") ---------------------------------------------------
 // VEC = 4: each thread moves four consecutive envs with int4 / uchar4 requests.
-template <int VEC>
+// SMEM: one shared level for the whole batch -- its three bit planes are staged in shared memory once
+// per block, so the (up to five) plane look-ups of a step never leave the SM.
+template <int VEC, bool SMEM = false>
 __global__ void __launch_bounds__(256)
 step_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restrict__ pos,
             int32_t* __restrict__ obs, int32_t* __restrict__ reward, uint8_t* __restrict__ done,
             const int32_t* __restrict__ start_choice, int64_t* stats, uint32_t flags) {
+  extern __shared__ uint32_t planes_s[];
+  if (SMEM) {
+    for (int w = threadIdx.x; w < lv.words; w += blockDim.x) {
+      planes_s[w] = __ldg(lv.wall + w);
+      planes_s[lv.words + w] = __ldg(lv.goal + w);
+      planes_s[2 * lv.words + w] = __ldg(lv.lava + w);
+    }
+    __syncthreads();
+    lv.wall = planes_s;
+    lv.goal = planes_s + lv.words;
+    lv.lava = planes_s + 2 * lv.words;
+  }
   const int64_t i0 = (static_cast<int64_t>(blockIdx.x) * blockDim.x + threadIdx.x) * VEC;
   const bool care = !(flags & GU_FLAG_NO_CARE_TERMINAL);
   const bool auto_reset = flags & GU_FLAG_AUTO_RESET;
@@ -33,7 +47,7 @@ step_kernel(LevelsView lv, const int32_t* __restrict__ actions, int32_t* __restr
     }
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      transition(lv, i0 + k, s[k], a[k], care, n[k], r[k], d[k]);
+      transition<SMEM>(lv, i0 + k, s[k], a[k], care, n[k], r[k], d[k]);
       nxt[k] = n[k];
       if (auto_reset && d[k]) nxt[k] = start_choice ? __ldg(start_choice + i0 + k) : start_of(lv, i0 + k);
       rsum += r[k];
@@ -318,11 +332,19 @@ extern "C" __attribute__((visibility("default"))) int gu_step(const gu_levels* l
       step_small_kernel<2><<<blocks, 256, 0, st>>>(v, actions, pos, pos, obs, reward, done, start_choice, stats, flags);
   } else if (vec) {
     const int64_t threads = n / 4;
-    step_kernel<4><<<static_cast<unsigned>((threads + 255) / 256), 256, 0, st>>>(
-        v, actions, pos, obs, reward, done, start_choice, stats, flags);
+    const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+    if (!lv->per_env && lv->words <= 4096)      // shared level: planes staged in shared memory (<= 48 KB)
+      step_kernel<4, true><<<blocks, 256, 3 * lv->words * sizeof(uint32_t), st>>>(v, actions, pos, obs, reward, done,
+                                                                                  start_choice, stats, flags);
+    else
+      step_kernel<4><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
   } else {
-    step_kernel<1><<<static_cast<unsigned>((n + 255) / 256), 256, 0, st>>>(
-        v, actions, pos, obs, reward, done, start_choice, stats, flags);
+    const unsigned blocks = static_cast<unsigned>((n + 255) / 256);
+    if (!lv->per_env && lv->words <= 4096 && n >= 256)
+      step_kernel<1, true><<<blocks, 256, 3 * lv->words * sizeof(uint32_t), st>>>(v, actions, pos, obs, reward, done,
+                                                                                  start_choice, stats, flags);
+    else
+      step_kernel<1><<<blocks, 256, 0, st>>>(v, actions, pos, obs, reward, done, start_choice, stats, flags);
   }
   GU_CHECK_LAUNCH();
   return GU_OK;

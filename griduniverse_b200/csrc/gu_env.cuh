@@ -31,8 +31,12 @@ inline int check_levels(const gu_levels* lv, int64_t n) {
   return GU_OK;
 }
 
+// SMEM: the planes of a shared level have been staged in shared memory by the block (plain loads;
+// the read-only global path does not apply to shared addresses)
+template <bool SMEM = false>
 __device__ __forceinline__ bool plane_bit(const uint32_t* __restrict__ plane, const LevelsView& lv,
                                           int64_t env, int s) {
+  if (SMEM) return (plane[s >> 5] >> (s & 31)) & 1u;
   const int64_t idx = lv.per_env ? static_cast<int64_t>(s >> 5) * lv.N + env : (s >> 5);
   return (__ldg(plane + idx) >> (s & 31)) & 1u;
 }
@@ -50,15 +54,16 @@ __device__ __forceinline__ int clamp_move(int s, int a, int X, int Y) {
 }
 
 // look_step_ahead (griduniverse_env.py:136-155)
+template <bool SMEM = false>
 __device__ __forceinline__ void transition(const LevelsView& lv, int64_t env, int s, int a, bool care,
                                            int& n, int& r, bool& term) {
   n = s;
-  const bool stay = care && (plane_bit(lv.goal, lv, env, s) || plane_bit(lv.lava, lv, env, s));
+  const bool stay = care && (plane_bit<SMEM>(lv.goal, lv, env, s) || plane_bit<SMEM>(lv.lava, lv, env, s));
   if (!stay) {
     const int c = clamp_move(s, a, lv.X, lv.Y);
-    if (!plane_bit(lv.wall, lv, env, c)) n = c;
+    if (!plane_bit<SMEM>(lv.wall, lv, env, c)) n = c;
   }
-  const bool g = plane_bit(lv.goal, lv, env, n), l = plane_bit(lv.lava, lv, env, n);
+  const bool g = plane_bit<SMEM>(lv.goal, lv, env, n), l = plane_bit<SMEM>(lv.lava, lv, env, n);
   r = reward_of(g, l);
   term = g | l;
 }
