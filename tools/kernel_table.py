@@ -62,7 +62,21 @@ def step():
 
 
 row("step, one per launch (29 B/step)", timeit(step, n=20), 29.0 * n)
-del acts, obs, rew, dn, env, lv
+packed, _ = env.pack_actions(acts)
+row("rollout, packed 2-bit actions (0.25 B/step), T=32", timeit(lambda: env.rollout(packed, per_env=True, packed_steps=T), n=10),
+    0.25 * n * T)
+del acts, obs, rew, dn, env, lv, packed
+venv = GridUniverseVecEnv(n, grid_shape=(8, 8), lava_states=[5, 17], walls=[9, 10, 20], auto_reset=True)
+a1 = torch.randint(0, 4, (n,), dtype=torch.int32, device="cuda")
+
+
+def step_shared():
+    L.gu_step(venv.levels.ref(), n, _cabi.ptr(a1), _cabi.ptr(venv.pos), _cabi.ptr(nxt), _cabi.ptr(r1), _cabi.ptr(t1), None,
+              _cabi.ptr(venv.stats), 1, _cabi.stream_ptr())
+
+
+row("step, shared level staged in smem (17 B/step)", timeit(step_shared, n=20), 17.0 * n)
+del venv, a1
 torch.cuda.empty_cache()
 
 # ---- planning kernels, cfg-5 grid ----------------------------------------------------------
@@ -86,3 +100,31 @@ for dt, sz in ((np.float32, 4), (np.float64, 8)):
         del probs
     del a, b, tie, pl, grid
     torch.cuda.empty_cache()
+
+# ---- batched small mazes (cfg 2 shape) and Monte-Carlo evaluation ----------------------------
+import json  # noqa: E402
+import random  # noqa: E402
+import time  # noqa: E402
+
+from griduniverse_b200.algorithms import monte_carlo  # noqa: E402
+from griduniverse_b200.batch import MazeBatch  # noqa: E402
+from griduniverse_b200.envs import GridUniverseEnv  # noqa: E402
+
+with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "levels.json")) as f:
+    LV = json.load(f)
+base = [GridUniverseEnv.from_text_lines(LV["gen10_%d" % k]).level for k in range(10)]
+for B in (148, 148 * 8, 148 * 32, 148 * 128):
+    mb = MazeBatch([base[i % 10] for i in range(B)])
+    ms = timeit(lambda: mb.value_iteration("uniform", None, 1e-6, 1000, 0.9), n=5)
+    ms2 = timeit(lambda: mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9), n=5)
+    print("batched 10x10 mazes B=%6d: VI %.3f ms (%.2e mazes/s)   PI %.3f ms (%.2e mazes/s)" % (B, ms, B / ms * 1e3, ms2, B / ms2 * 1e3))
+env = GridUniverseEnv.from_text_lines(LV["maze_21x21"])
+pol = np.ones((env.world.size, 4)) / 4
+for per in (1, 256):
+    random.seed(0)
+    np.random.seed(0)
+    monte_carlo.monte_carlo_evaluation(pol, env, num_episodes=20, verbose=False, episodes_per_launch=per)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    monte_carlo.monte_carlo_evaluation(pol, env, num_episodes=100, verbose=False, episodes_per_launch=per)
+    print("monte_carlo_evaluation maze_21x21, 100 episodes, %3d per launch: %.1f ms" % (per, (time.perf_counter() - t0) * 1e3))
