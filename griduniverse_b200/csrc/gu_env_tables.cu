@@ -104,6 +104,14 @@ pack_nt16_kernel(LevelsView lv, uint16_t* __restrict__ tables) {
 // selectable (GU_INFO8_RING=deep) for experiments.
 struct RingStd { static constexpr int kRows = GU_INFO8_ROWS, kStages = GU_INFO8_STAGES, kWarps = GU_ROLLOUT_WARPS; };
 struct RingDeep { static constexpr int kRows = 16, kStages = 4, kWarps = 2; };
+// One env per lane (small batches): a box of 8 steps is consumed in ~600 cycles, less than a DRAM round
+// trip under load, so with two stages every box wait is exposed.  Four stages of the same 8-row box put
+// three box times between a tile's issue and its use and still leave 16 warps per SM resident for a
+// 16x16 level (12 KB per warp), which the 16-row ring above does not.
+struct RingMid { static constexpr int kRows = 8, kStages = 4, kWarps = 4; };
+#ifndef GU_INFO8_PATCH
+#define GU_INFO8_PATCH 1
+#endif
 
 __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
   uint32_t v;
@@ -145,9 +153,14 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
   const bool accumulate = flags & GU_FLAG_ACCUMULATE;
   const int Trows = PACKED ? (T + 15) / 16 : T;                       // rows of the action matrix
   const int nbatch = (Trows + kInfoRows - 1) / kInfoRows;
-  // signed byte LUT of the four moves: UP -X, RIGHT +1, DOWN +X, LEFT -1
-  const uint32_t deltas = (static_cast<uint32_t>(-X) & 0xffu) | (1u << 8) | ((static_cast<uint32_t>(X) & 0xffu) << 16) |
-                          (0xffu << 24);
+  // per action: {bit of the info byte that says "a moves", scaled position delta}: UP -X, RIGHT +1, DOWN +X, LEFT -1
+  __shared__ __align__(8) int2 act_lut[4];
+  if (threadIdx.x < 4) {
+    const int a = threadIdx.x;
+    act_lut[a] = make_int2(1 << a, 8 * (a == 0 ? -X : (a == 1 ? 1 : (a == 2 ? X : -1))));
+  }
+  __syncthreads();
+  const uint32_t lut_s = smem_u32(&act_lut[0]);
   long long rsum = 0, dcnt = 0;
 
   if (env0 < N) {
@@ -166,58 +179,105 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
         if (SC) tma_load_2d(act_s + b * kBoxBytes + kActBytes, &sc_map, env0, b * kInfoRows, bar0 + 8 * b);
       }
     }
-    int p[EPT], st[EPT];
+    // The position travels pre-scaled, q = 8 * cell: the funnel shift that brings the cell's byte down takes
+    // q itself (amount modulo 32) and the row offset of its table word is (q & ~31) * (ROWB / 32) -- one
+    // mask and one multiply-add (FMA pipe) on the dependent chain position -> table word -> landing cell.
+    // The kernels are bound by the half-rate ALU pipe (cfg 4, packed actions: 92 %) or by that chain under
+    // contention for it (BASELINE cfg 3: 14 warps per SM, 1024 sequential steps), so ALU-pipe instructions
+    // per step are what counts.
+    constexpr int QS = 8, QLOG = 3;
+    // With auto-reset to a fixed start the reset of the info byte leaves the chain as well: once the
+    // table is staged every lane rewrites the "action moves" nibble of the TERMINAL cells of its envs to
+    // the start cell's nibble, so the byte fetched for a terminal landing cell already is the byte the
+    // next step needs (its goal / lava bits still count the episode end); only the position is selected.
+    constexpr bool kPatch = GU_INFO8_PATCH && AUTO_RESET && !SC;
+    int q[EPT], stq[EPT];
     uint32_t inf[EPT], inf_st[EPT], fsum[EPT], fsq[EPT];
     uint32_t tabk[EPT];                              // shared-memory byte address of the env's column
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
-      p[k] = pos[env0 + k * 32 + lane];
-      st[k] = (AUTO_RESET && !SC) ? start[env0 + k * 32 + lane] : 0;      // lv->start may be NULL otherwise
+      q[k] = pos[env0 + k * 32 + lane] * QS;
+      stq[k] = (AUTO_RESET && !SC) ? start[env0 + k * 32 + lane] * QS : 0;      // lv->start may be NULL otherwise
       fsum[k] = 0;
       fsq[k] = 0;
       tabk[k] = tab_s + (k * 32 + lane) * 4;
     }
     mbar_wait(bar_tab, 0);
-    // info byte of cell c: word c >> 2 of the env's column (rows are ROWB bytes apart), byte c & 3
-    // (funnel shift, amount taken modulo 32)
+    // info byte of the cell at scaled position c = 8 * cell: word cell >> 2 of the env's column (rows are
+    // ROWB bytes apart), byte cell & 3
     auto info_at = [&](int k, int c) -> uint32_t {
-      const uint32_t word = lds_u32(tabk[k] + (static_cast<uint32_t>(c) & ~3u) * (ROWB / 4));
-      return __funnelshift_r(word, 0u, static_cast<uint32_t>(c) << 3);
+      uint32_t a;                                   // kept as mask + multiply-add: the compiler's shift + mask + add is one deeper
+      asm("{\n\t"
+          ".reg .b32 t;\n\t"
+          "and.b32 t, %1, 0xffffffe0;\n\t"
+          "mad.lo.u32 %0, t, %2, %3;\n\t"
+          "}"
+          : "=r"(a)
+          : "r"(c), "n"(ROWB / 32), "r"(tabk[k]));
+      const uint32_t word = lds_u32(a);
+      return __funnelshift_r(word, 0u, static_cast<uint32_t>(c));
     };
 #pragma unroll
     for (int k = 0; k < EPT; ++k) {
-      inf[k] = info_at(k, p[k]);
-      inf_st[k] = (AUTO_RESET && !SC) ? info_at(k, st[k]) : 0u;
+      inf[k] = info_at(k, q[k]);
+      inf_st[k] = (AUTO_RESET && !SC) ? info_at(k, stq[k]) : 0u;
+    }
+    if constexpr (kPatch) {
+#pragma unroll
+      for (int k = 0; k < EPT; ++k) {
+        const uint32_t nib = (inf_st[k] & 0xfu) * 0x01010101u;
+        for (int w = 0; w < words; ++w) {
+          const uint32_t a = tabk[k] + static_cast<uint32_t>(w) * ROWB;
+          const uint32_t word = lds_u32(a);
+          const uint32_t term = (word | (word << 1)) & 0x80808080u;      // goal 0x40 | lava 0x80 per byte
+          if (term) {
+            const uint32_t m = (term >> 7) * 0x0fu;
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"((word & ~m) | (nib & m)) : "memory");
+          }
+        }
+      }
     }
 
-    auto step_one = [&](int k, uint32_t a, int t, uint32_t sc_addr) {
-      const uint32_t allowed = (inf[k] >> a) & 1u;
-      // sign-extended byte a of the delta LUT (PRMT, sign-replicate mode in the upper nibbles)
-      int d, n;
-      asm("prmt.b32 %0, %1, 0, %2;" : "=r"(d) : "r"(deltas), "r"(a * 0x1111u + 0x8880u));
-      asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(n) : "r"(static_cast<int>(allowed)), "r"(d), "r"(p[k]));
+    // `la` = 8 * action: byte offset into the block's {1 << a, 8 * delta[a]} table (one 8-byte shared load
+    // instead of a shift, a multiply and a PRMT per step)
+    auto step_one = [&](int k, uint32_t la, int t, uint32_t sc_addr) {
+      uint32_t abit;
+      int ds;
+      asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(abit), "=r"(ds) : "r"(lut_s + la));
+      // bit a of the current cell's info byte: the action moves.  One predicate-setting LOP3 and one
+      // predicated add on the chain (the compiler's own form, shift + mask + compare + select + add, is 5 deep).
+      int n = q[k];
+      asm("{\n\t"
+          ".reg .pred mv;\n\t"
+          ".reg .b32 t;\n\t"
+          "and.b32 t, %1, %2;\n\t"
+          "setp.ne.u32 mv, t, 0;\n\t"
+          "@mv add.s32 %0, %0, %3;\n\t"
+          "}"
+          : "+r"(n)
+          : "r"(inf[k]), "r"(abit), "r"(ds));
       uint32_t i2 = info_at(k, n);
       const uint32_t f = i2 & 0xc0u;               // goal 0x40 / lava 0x80 of the landing cell
       if (TRAJ) {
         const int64_t o = static_cast<int64_t>(t) * N + env0 + k * 32 + lane;
-        if (obs) obs[o] = n;
+        if (obs) obs[o] = n >> QLOG;
         if (reward) reward[o] = (f & 0x80u) ? kRewardLava : ((f & 0x40u) ? kRewardGoal : kRewardStep);
         if (done) done[o] = f ? 1 : 0;
       }
       fsum[k] += f;                               // 64*goals + 128*lavas
       fsq[k] += f * f;                            // 4096*goals + 16384*lavas
       if (AUTO_RESET && f) {
-        if (SC) { n = static_cast<int>(lds_u32(sc_addr + k * 128)); i2 = info_at(k, n); }
-        else { n = st[k]; i2 = inf_st[k]; }
+        if (SC) { n = static_cast<int>(lds_u32(sc_addr + k * 128)) * QS; i2 = info_at(k, n); }
+        else { n = stq[k]; if (!kPatch) i2 = inf_st[k]; }
       }
-      p[k] = n;
+      q[k] = n;
       inf[k] = i2;
     };
     // one row of the action matrix: one step (int32 actions) or sixteen (packed)
     auto step_row = [&](uint32_t arow, int row, bool full) {   // arow: smem address of this lane's word in the row
       if (!PACKED) {
 #pragma unroll
-        for (int k = 0; k < EPT; ++k) step_one(k, lds_u32(arow + k * 128) & 3u, row, arow + kActBytes);
+        for (int k = 0; k < EPT; ++k) step_one(k, (lds_u32(arow + k * 128) << 3) & 24u, row, arow + kActBytes);
       } else {
         uint32_t w[EPT];
 #pragma unroll
@@ -226,12 +286,13 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
 #pragma unroll
           for (int s = 0; s < 16; ++s) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s, 0u);
+            for (int k = 0; k < EPT; ++k)
+              step_one(k, (s == 0 ? w[k] << 3 : (s == 1 ? w[k] << 1 : w[k] >> (2 * s - 3))) & 24u, row * 16 + s, 0u);
           }
         } else {
           for (int s = 0; row * 16 + s < T; ++s) {
 #pragma unroll
-            for (int k = 0; k < EPT; ++k) step_one(k, (w[k] >> (2 * s)) & 3u, row * 16 + s, 0u);
+            for (int k = 0; k < EPT; ++k) step_one(k, ((w[k] >> (2 * s)) & 3u) << 3, row * 16 + s, 0u);
           }
         }
       }
@@ -266,7 +327,7 @@ rollout_info8_tma_kernel(const __grid_constant__ CUtensorMap act_map, const __gr
       rsum += ret;
       dcnt += dones;
       const int e = env0 + k * 32 + lane;
-      pos[e] = p[k];
+      pos[e] = q[k] >> QLOG;
       if (env_return) env_return[e] = static_cast<int>(ret) + (accumulate ? env_return[e] : 0);
       if (env_done) env_done[e] = static_cast<int>(dones) + (accumulate ? env_done[e] : 0);
     }
@@ -458,6 +519,8 @@ int rollout_tables(const gu_levels* lv, int64_t n, int64_t T, const int32_t* act
     if (ept == 4) GU_INFO8(4, RingStd);
     if (ept == 2) GU_INFO8(2, RingStd);
     if (deep) GU_INFO8(1, RingDeep);
+    static const bool mid_off = ring_env && ring_env[0] == 's';   // developer switch: "std"
+    if (!mid_off && info8_smem_bytes<RingMid>((cells + 3) / 4, 1) <= 56 * 1024) GU_INFO8(1, RingMid);
     GU_INFO8(1, RingStd);
 #undef GU_INFO8
 #undef GU_INFO8_P

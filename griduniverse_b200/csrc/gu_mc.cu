@@ -88,38 +88,81 @@ mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* 
                    double alpha, int cells, int32_t* __restrict__ obs, int32_t* __restrict__ rew,
                    double* __restrict__ G, double* __restrict__ total_visits, double* __restrict__ total_return,
                    double* __restrict__ value, int32_t* __restrict__ lengths, uint8_t* __restrict__ done,
-                   long long* __restrict__ meta) {
+                   long long* __restrict__ meta, int use_smem) {
   __shared__ int L_sh, stop_sh;
   __shared__ long long off_sh;
+  // Level small enough (dynamic shared memory was granted): the CDF rows and a (cell, action) ->
+  // landing cell / reward / done table are staged once, so a step of the sequential walk costs two
+  // shared-memory round trips instead of eight dependent global loads.
+  extern __shared__ __align__(16) double mc_smem[];
+  const bool staged = use_smem != 0;
+  double* cdf_s = mc_smem;                                             // [cells][4]
+  uint16_t* nt_s = reinterpret_cast<uint16_t*>(mc_smem + 4 * cells);   // [cells][4]: landing | goal << 14 | lava << 15
   const int tid = threadIdx.x;
+  if (staged) {
+    for (int i = tid; i < cells * 4; i += kMcThreads) {
+      cdf_s[i] = __ldg(cdf + i);
+      int n, r;
+      bool d;
+      transition(lv, 0, i >> 2, i & 3, true, n, r, d);
+      nt_s[i] = static_cast<uint16_t>(n | (r == kRewardGoal ? 0x4000 : 0) | (r == kRewardLava ? 0x8000 : 0));
+    }
+  }
   if (tid == 0) { off_sh = 0; stop_sh = 0; }
   __syncthreads();
   int e = 0;
   for (; e < E; ++e) {
     const int start = __ldg(starts + e);
-    if (tid == 0) {
-      int s = start, t = 0;
+    if (tid < 32) {
+      // Warp 0 walks the episode in lockstep -- every lane holds the same state, lane 0 writes -- so that
+      // the uniform draws can be fetched 32 at a time, one per lane and one window ahead, and handed to the
+      // step by warp shuffle: no global-memory round trip on the sequential chain state -> action -> state.
+      int s = start, t = 0, stop = 0;
       bool d = false;
       const long long off = off_sh;
-      for (; t < T && !d; ++t) {
-        if (off + t >= n_uniforms) { stop_sh = 1; break; }            // out of draws: the host continues
-        const double* row = cdf + static_cast<int64_t>(s) * 4;
-        if (__ldg(row + 3) != __ldg(row + 3)) { stop_sh = 2 + s; break; }   // np.random.choice would raise here
-        const double u = __ldg(uniforms + off + t);
-        const int a = (__ldg(row) <= u) + (__ldg(row + 1) <= u) + (__ldg(row + 2) <= u);
-        int n, r;
-        transition(lv, 0, s, a, true, n, r, d);
-        obs[t] = n;
-        rew[t] = r;
-        s = n;
+      double ucur = off + tid < n_uniforms ? __ldg(uniforms + off + tid) : 0.0;
+      while (t < T && !d && stop == 0) {
+        const long long nx = off + t + 32 + tid;
+        const double unext = nx < n_uniforms ? __ldg(uniforms + nx) : 0.0;
+        const int wend = min(t + 32, T);
+        for (; t < wend && !d; ++t) {
+          if (off + t >= n_uniforms) { stop = 1; break; }              // out of draws: the host continues
+          const double u = __shfl_sync(0xffffffffu, ucur, t & 31);
+          int n, r;
+          if (staged) {
+            const double2 c01 = *reinterpret_cast<const double2*>(cdf_s + s * 4);
+            const double2 c23 = *reinterpret_cast<const double2*>(cdf_s + s * 4 + 2);
+            const uint2 ntr = *reinterpret_cast<const uint2*>(nt_s + s * 4);   // the four landing entries of s
+            if (c23.y != c23.y) { stop = 2 + s; break; }               // np.random.choice would raise here
+            const int a = (c01.x <= u) + (c01.y <= u) + (c23.x <= u);
+            const uint32_t e = (((a & 2) ? ntr.y : ntr.x) >> ((a & 1) * 16)) & 0xffffu;
+            n = static_cast<int>(e & 0x3fffu);
+            r = (e & 0x8000u) ? kRewardLava : ((e & 0x4000u) ? kRewardGoal : kRewardStep);
+            d = (e & 0xc000u) != 0;
+          } else {
+            const double* row = cdf + static_cast<int64_t>(s) * 4;
+            if (__ldg(row + 3) != __ldg(row + 3)) { stop = 2 + s; break; }
+            const int a = (__ldg(row) <= u) + (__ldg(row + 1) <= u) + (__ldg(row + 2) <= u);
+            transition(lv, 0, s, a, true, n, r, d);
+          }
+          if (tid == 0) {
+            obs[t] = n;
+            rew[t] = r;
+          }
+          s = n;
+        }
+        ucur = unext;
       }
-      if (stop_sh == 0) {
-        L_sh = t;
-        off_sh = off + t;
-        lengths[e] = t;
-        done[e] = d;
-      } else if (stop_sh >= 2) {
-        off_sh = off + t;                       // draws consumed before the failing step
+      if (tid == 0) {
+        stop_sh = stop;
+        if (stop == 0) {
+          L_sh = t;
+          off_sh = off + t;
+          lengths[e] = t;
+          done[e] = d;
+        } else if (stop >= 2) {
+          off_sh = off + t;                     // draws consumed before the failing step
+        }
       }
     }
     __syncthreads();
@@ -181,10 +224,18 @@ extern "C" __attribute__((visibility("default"))) int gu_mc_evaluate_f64(
       !total_return || !value || !lengths || !done || !meta)
     return GU_ERR_NULL;
   if (n_episodes < 0 || max_steps < 0 || n_uniforms < 0 || mode < 0 || mode > 2) return GU_ERR_SHAPE;
-  mc_evaluate_kernel<<<1, kMcThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+  const int cells = lv->X * lv->Y;
+  const size_t smem = static_cast<size_t>(cells) * 40;                 // 4 f64 + 4 u16 per cell
+  const int use_smem = cells <= 16383 && smem <= 200 * 1024;
+  if (use_smem && smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(mc_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         static_cast<int>(smem));
+    if (e != cudaSuccess) return static_cast<int>(e);
+  }
+  mc_evaluate_kernel<<<1, kMcThreads, use_smem ? smem : 0, static_cast<cudaStream_t>(stream)>>>(
       view_of(lv, 1), cdf, uniforms, n_uniforms, starts, n_episodes, max_steps, weights, keep, every_visit, mode, alpha,
-      lv->X * lv->Y, obs_scratch, rew_scratch, g_scratch, total_visits, total_return, value, lengths, done,
-      reinterpret_cast<long long*>(meta));
+      cells, obs_scratch, rew_scratch, g_scratch, total_visits, total_return, value, lengths, done,
+      reinterpret_cast<long long*>(meta), use_smem);
   GU_CHECK_LAUNCH();
   return GU_OK;
 }

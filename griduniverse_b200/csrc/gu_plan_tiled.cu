@@ -206,6 +206,26 @@ __device__ __forceinline__ void backup_ties_pair(const float (&ra0)[4], const fl
   out1 = acc.y;
 }
 
+// Greedy extraction: one tie of action a in cell j of a cell pair adds k = 2^(a + 8 j) to a magic-number
+// accumulator.  f32: FSET (1.0 / 0.0) feeding an FFMA; f64: the compare predicates an FADD.
+#ifndef GU_TIE_FMA
+#define GU_TIE_FMA 1
+#endif
+__device__ __forceinline__ void tie_accumulate(float ra, float m, float k, float& acc) {
+  float w;
+  asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(w) : "f"(ra), "f"(m));
+  acc = __fmaf_rn(w, k, acc);
+}
+__device__ __forceinline__ void tie_accumulate(double ra, double m, float k, float& acc) {
+  asm("{\n\t"
+      ".reg .pred t;\n\t"
+      "setp.eq.f64 t, %1, %2;\n\t"
+      "@t add.rn.f32 %0, %0, %3;\n\t"
+      "}"
+      : "+f"(acc)
+      : "d"(ra), "d"(m), "f"(k));
+}
+
 #ifndef GU_TILED_WARPS
 #define GU_TILED_WARPS 4
 #endif
@@ -790,7 +810,35 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
               for (int k = 0; k < IW; ++k) pm[k] = *reinterpret_cast<const uint32_t*>(pp + 4 * k);
             }
           }
-          if constexpr (kPack && KIND == GU_POLICY_GREEDY && !WRITE_TIE) {
+          if constexpr (WRITE_TIE && GU_TIE_FMA) {
+            // Greedy extraction: the kernel is bound by the half-rate ALU pipe (selects, compares, bit
+            // assembly), so the tie mask is assembled on the FMA pipe instead: every tie adds 2^(a + 8 j)
+            // to a magic-number accumulator (2^23: the integer lands in the low mantissa bits), two cells
+            // per accumulator, and one PRMT puts the four masks of an info word together.  Terminal
+            // cells (all four actions blocked, so all four tie) are cleared with word-wide bit
+            // arithmetic on the goal / lava bits instead of a NaN "poison" added to every max.
+#pragma unroll
+            for (int k = 0; k < IW; ++k) {
+              float acc2[2] = {8388608.0f, 8388608.0f};
+#pragma unroll
+              for (int j = 0; j < 4 && 4 * k + j < CPT; ++j) {
+                const int c = 4 * k + j;
+                const uint32_t inf = info_of(cur.info, c);
+                const T rts = cur.rt[c];
+                T ra[4];
+                ra[0] = (inf & kBlkU) ? rts : up.rt[c];
+                ra[1] = (inf & kBlkR) ? rts : (c == CPT - 1 ? cur.rtr : cur.rt[c + 1 < CPT ? c + 1 : c]);
+                ra[2] = (inf & kBlkD) ? rts : dn.rt[c];
+                ra[3] = (inf & kBlkL) ? rts : (c == 0 ? cur.rtl : cur.rt[c > 0 ? c - 1 : c]);
+                const T m = max_nn(max_nn(ra[0], ra[1]), max_nn(ra[2], ra[3]));
+#pragma unroll
+                for (int a = 0; a < 4; ++a) tie_accumulate(ra[a], m, static_cast<float>(1u << (a + 8 * (j & 1))), acc2[j >> 1]);
+              }
+              const uint32_t word = __byte_perm(__float_as_uint(acc2[0]), __float_as_uint(acc2[1]), 0x5410u);
+              const uint32_t term = (cur.info[k] | (cur.info[k] << 1)) & 0x10101010u;   // goal (bit 3) | lava (bit 4)
+              ties[k] = word & ~((term >> 4) * 15u);                                    // utils.py:70: all-zero rows
+            }
+          } else if constexpr (kPack && KIND == GU_POLICY_GREEDY && !WRITE_TIE) {
 #pragma unroll
             for (int c = 0; c < CPT; c += 2) {
               float ga[2][4], ra[2][4], m[2];

@@ -88,11 +88,12 @@ for dt, sz in ((np.float32, 4), (np.float64, 8)):
     a, b = grid.empty(), grid.empty()
     a.normal_()
     tie = pl.greedy(a, 0.9)
+    tie2 = grid.empty(torch.uint8)     # extraction is timed into a persistent buffer: the kernel alone, no memset
     name = np.dtype(dt).name
     row("%s sweep, fused greedy" % name, timeit(lambda: pl.sweep(a, b, 3, None, 0.9)), (2 * sz + 0.375) * cells)
     row("%s sweep, uniform policy" % name, timeit(lambda: pl.sweep(a, b, 2, None, 0.9)), (2 * sz + 0.375) * cells)
     row("%s sweep, tie-mask policy (+1 B)" % name, timeit(lambda: pl.sweep(a, b, 1, tie, 0.9)), (2 * sz + 1.375) * cells)
-    row("%s greedy extraction" % name, timeit(lambda: pl.greedy(a, 0.9)), (sz + 1.375) * cells)
+    row("%s greedy extraction" % name, timeit(lambda: pl.greedy(a, 0.9, tie2)), (sz + 1.375) * cells)
     if dt == np.float32:
         probs = torch.full((grid.rows + 2, grid.pitch, 4), 0.25, dtype=grid.dtype, device="cuda")
         row("%s sweep, [N,4] probabilities (+16 B)" % name, timeit(lambda: pl.sweep(a, b, 0, probs, 0.9)),
