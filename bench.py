@@ -644,8 +644,9 @@ def small_configs(dev, world):
 
 
 def run_profile(args):
-    """Short run for ncu (never a bench number): 2 rollout passes of the cfg-4 shape, a few sweeps
-    of each kind, one greedy extraction and eight breadth-first levels on the cfg-5 grid."""
+    """Short run for ncu (never a bench number): 2 rollout passes of the cfg-4 shape (+ one with packed
+    actions, one step), one cfg-3 pass, the batched small-maze solvers, a few sweeps of each kind, one
+    greedy extraction and eight breadth-first levels on the cfg-5 grid."""
     import torch
     from griduniverse_b200 import synth
     from griduniverse_b200.envs import GridUniverseVecEnv
@@ -661,7 +662,13 @@ def run_profile(args):
     packed, _ = env.pack_actions(actions)
     env.rollout(packed, trajectories=False, per_env=True, packed_steps=ENV_T)
     env.step(actions[0])
-    del actions, packed
+    del actions, packed, env, levels
+    # cfg 3: 65,536 16x16 envs, T = 1024 (one env per lane, 4-stage ring)
+    lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
+    env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
+    a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev)
+    env3.rollout(a3, per_env=True)
+    del a3, env3, lv3
     # cfg 2 in batch form: 4,736 10x10 mazes, one block each
     from griduniverse_b200.batch import MazeBatch
     from griduniverse_b200.envs import GridUniverseEnv
@@ -678,7 +685,7 @@ def run_profile(args):
         a, b = grid.empty(), grid.empty()
         res = pl.new_residuals(4)
         pl.sweep(a, b, 2, None, VI_GAMMA, res[0:1])
-        for i in range(3):
+        for i in range(2):
             pl.sweep(b if i % 2 == 0 else a, a if i % 2 == 0 else b, 3, None, VI_GAMMA, res[i + 1:i + 2])
         tie = pl.greedy(a, VI_GAMMA)
         pl.sweep(a, b, 1, tie, VI_GAMMA)
