@@ -20,7 +20,7 @@ GU_BFS_LAVA_BLOCKS = 1
 GU_TEXT_NO_START, GU_TEXT_NO_GOAL = -1, -2
 GU_POLICY_PROBS, GU_POLICY_MASK, GU_POLICY_UNIFORM, GU_POLICY_GREEDY = 0, 1, 2, 3
 
-EXPORTS = ("gu_step", "gu_rollout", "gu_pack_actions", "gu_pack_actions_host", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_evaluate_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead",
+EXPORTS = ("gu_step", "gu_rollout", "gu_pack_actions", "gu_pack_actions_host", "gu_rollout_policy", "gu_mc_episode_f64", "gu_mc_evaluate_f64", "gu_mc_finalize_f64", "gu_synth_env_levels", "gu_synth_maze", "gu_tables_bytes", "gu_pack_tables", "gu_look_step_ahead", "gu_look_server_start",
            "gu_sweep_f64", "gu_sweep_f32", "gu_greedy_f64", "gu_greedy_f32", "gu_pack_info", "gu_sweep_peer_f32", "gu_sweep_peer_f64", "gu_peer_wait", "gu_max_diff_f32", "gu_max_diff_f64", "gu_vi_small_f64",
            "gu_vi_small_max_cells", "gu_pi_small_f64", "gu_pi_small_max_cells", "gu_vi_batch_f64", "gu_pi_batch_f64", "gu_bfs_init", "gu_bfs_expand", "gu_bfs_walk", "gu_pack_level_text", "gu_render_ansi", "gu_render_rgb", "gu_version", "gu_arch", "gu_error_string")
 
@@ -103,6 +103,7 @@ def lib():
         "gu_tables_bytes": (i64, [lvp, i64]),
         "gu_pack_tables": (ctypes.c_int, [lvp, i64, p, u32, p]),
         "gu_look_step_ahead": (ctypes.c_int, [lvp, i64, p, p, p, p, p, u32, p]),
+        "gu_look_server_start": (ctypes.c_int, [lvp, p, u32, i64, i64, p]),
         "gu_sweep_f64": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f64, p, p, f64, p]),
         "gu_sweep_f32": (ctypes.c_int, [gp, p, p, ctypes.c_int, p, f32, p, p, f32, p]),
         "gu_pack_info": (ctypes.c_int, [gp, p, p]),

@@ -183,6 +183,49 @@ look_kernel(LevelsView lv, int64_t m, const int32_t* __restrict__ states,
   if (terminal) terminal[i] = d;
 }
 
+// ---- resident look_step_ahead service for the one-env step loop --------------------------------------
+// The reference's `env.step(a)` is one (state, action) -> (next, reward, done) lookup
+// (griduniverse_env.py:176-185).  One launch + one stream synchronise per lookup costs ~20 us; this kernel
+// instead stays resident while requests keep coming and answers each one over PCIe: the host writes an
+// 8-byte request word into a pinned mailbox, thread 0 polls it (system-scope loads), evaluates the same
+// transition() every other kernel uses, and stores the 16-byte answer back into the mailbox; the host
+// spins on the answer's sequence number.  The kernel leaves by itself after `idle_cycles` without a
+// request (and in any case after `max_cycles`), clearing the mailbox's `alive` word, so device-wide
+// synchronisation points are never held up for long; the host relaunches it on demand.
+//   mailbox (32 x uint32, 128-byte aligned, pinned host memory):
+//     [0:2]   request, one uint64: bits 0-31 sequence number, 32-33 action, 34 "do not care about
+//             terminals" (care_about_terminal=False), 35-63 state
+//     [16:20] answer, one 16-byte store: {sequence number, next state, reward, terminal}
+//     [20]    alive: set by the host before the launch, cleared by the kernel when it leaves
+__global__ void __launch_bounds__(32)
+look_server_kernel(LevelsView lv, const uint64_t* req, uint32_t* ack, uint32_t* alive, uint32_t seq0,
+                   long long idle_cycles, long long max_cycles) {
+  if (threadIdx.x != 0) return;
+  uint32_t last = seq0;
+  const long long born = clock64();
+  long long idle_since = born;
+  for (;;) {
+    uint64_t r;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(r) : "l"(req) : "memory");
+    const uint32_t seq = static_cast<uint32_t>(r);
+    if (seq != last) {
+      const uint32_t hi = static_cast<uint32_t>(r >> 32);
+      int n, rew;
+      bool term;
+      transition(lv, 0, static_cast<int>(hi >> 3), static_cast<int>(hi & 3u), (hi & 4u) == 0, n, rew, term);
+      asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(ack), "r"(seq), "r"(n), "r"(rew),
+                   "r"(term ? 1u : 0u) : "memory");
+      last = seq;
+      idle_since = clock64();
+    } else {
+      const long long now = clock64();
+      if (now - idle_since > idle_cycles || now - born > max_cycles) break;
+    }
+  }
+  __threadfence_system();
+  asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(alive), "r"(0u) : "memory");
+}
+
 // Policy-driven episodes (monte_carlo.py:7-26): one thread per episode, shared level.
 __global__ void __launch_bounds__(256)
 rollout_policy_kernel(LevelsView lv, int64_t T, const double* __restrict__ cdf,
@@ -411,6 +454,22 @@ extern "C" __attribute__((visibility("default"))) int gu_look_step_ahead(const g
   }
   look_kernel<<<static_cast<unsigned>((m + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       view_of(lv, m), m, states, actions, next, reward, terminal, flags);
+  GU_CHECK_LAUNCH();
+  return GU_OK;
+}
+
+extern "C" __attribute__((visibility("default"))) int gu_look_server_start(const gu_levels* lv, void* mailbox,
+                                                                           uint32_t seq0, int64_t idle_cycles,
+                                                                           int64_t max_cycles, void* stream) {
+  int rc = check_levels(lv, 1);
+  if (rc) return rc;
+  if (lv->per_env) return GU_ERR_UNSUPPORTED;
+  if (!mailbox) return GU_ERR_NULL;
+  if (reinterpret_cast<uintptr_t>(mailbox) & 127u) return GU_ERR_ALIGN;
+  if (static_cast<int64_t>(lv->X) * lv->Y > (1ll << 29) || idle_cycles <= 0 || max_cycles <= 0) return GU_ERR_SHAPE;
+  uint32_t* mb = static_cast<uint32_t*>(mailbox);
+  look_server_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(
+      view_of(lv, 1), reinterpret_cast<const uint64_t*>(mb), mb + 16, mb + 20, seq0, idle_cycles, max_cycles);
   GU_CHECK_LAUNCH();
   return GU_OK;
 }

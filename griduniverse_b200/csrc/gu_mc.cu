@@ -79,7 +79,8 @@ mc_finalize_kernel(int cells, const double* __restrict__ total_visits,
 // the per-state accumulation / update, in exactly the order of mc_returns_kernel / mc_update_kernel.
 // No host round trip per episode; the host reads the lengths, done flags and the number of draws
 // consumed once per launch.
-constexpr int kMcThreads = 256;
+constexpr int kMcThreads = 1024;      // the return and per-state passes are one visit index / one state per thread
+constexpr int kMcMaxStagedT = 4096;   // episodes up to this cap keep masked weights + rewards in shared memory
 
 __global__ void __launch_bounds__(kMcThreads)
 mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* __restrict__ uniforms,
@@ -88,7 +89,7 @@ mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* 
                    double alpha, int cells, int32_t* __restrict__ obs, int32_t* __restrict__ rew,
                    double* __restrict__ G, double* __restrict__ total_visits, double* __restrict__ total_return,
                    double* __restrict__ value, int32_t* __restrict__ lengths, uint8_t* __restrict__ done,
-                   long long* __restrict__ meta, int use_smem) {
+                   long long* __restrict__ meta, int use_smem, int use_wr) {
   __shared__ int L_sh, stop_sh;
   __shared__ long long off_sh;
   // Level small enough (dynamic shared memory was granted): the CDF rows and a (cell, action) ->
@@ -96,9 +97,16 @@ mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* 
   // shared-memory round trips instead of eight dependent global loads.
   extern __shared__ __align__(16) double mc_smem[];
   const bool staged = use_smem != 0;
-  double* cdf_s = mc_smem;                                             // [cells][4]
-  uint16_t* nt_s = reinterpret_cast<uint16_t*>(mc_smem + 4 * cells);   // [cells][4]: landing | goal << 14 | lava << 15
+  // use_wr: the discount weights, zeroed where the reference drops the term (a zero weight adds +-0 to the
+  // running sum, which leaves it bit-identical), and the episode's rewards as doubles live in shared
+  // memory, so the truncated-return pass is a branch-free multiply-add loop over shared operands
+  double* wk_s = mc_smem;                                              // [T]
+  double* rs_s = mc_smem + (use_wr ? T : 0);                           // [T]
+  double* cdf_s = mc_smem + (use_wr ? 2 * T : 0);                      // [cells][4]
+  uint16_t* nt_s = reinterpret_cast<uint16_t*>(cdf_s + 4 * cells);     // [cells][4]: landing | goal << 14 | lava << 15
   const int tid = threadIdx.x;
+  if (use_wr)
+    for (int i = tid; i < T; i += kMcThreads) wk_s[i] = __ldg(keep + i) ? __ldg(weights + i) : 0.0;
   if (staged) {
     for (int i = tid; i < cells * 4; i += kMcThreads) {
       cdf_s[i] = __ldg(cdf + i);
@@ -147,7 +155,8 @@ mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* 
           }
           if (tid == 0) {
             obs[t] = n;
-            rew[t] = r;
+            if (use_wr) rs_s[t] = static_cast<double>(r);
+            else rew[t] = r;
           }
           s = n;
         }
@@ -171,8 +180,14 @@ mc_evaluate_kernel(LevelsView lv, const double* __restrict__ cdf, const double* 
     for (int idx = tid; idx <= L; idx += kMcThreads) {                 // G[idx] (:69-70)
       double acc = 0.0;
       const int n = L - idx;
-      for (int i = 0; i < n; ++i)
-        if (__ldg(keep + i)) acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + i), static_cast<double>(rew[idx + i])));
+      if (use_wr) {
+        const double* r = rs_s + idx;
+#pragma unroll 8
+        for (int i = 0; i < n; ++i) acc = __dadd_rn(acc, __dmul_rn(wk_s[i], r[i]));
+      } else {
+        for (int i = 0; i < n; ++i)
+          if (__ldg(keep + i)) acc = __dadd_rn(acc, __dmul_rn(__ldg(weights + i), static_cast<double>(rew[idx + i])));
+      }
       G[idx] = acc;
     }
     __syncthreads();
@@ -225,17 +240,20 @@ extern "C" __attribute__((visibility("default"))) int gu_mc_evaluate_f64(
     return GU_ERR_NULL;
   if (n_episodes < 0 || max_steps < 0 || n_uniforms < 0 || mode < 0 || mode > 2) return GU_ERR_SHAPE;
   const int cells = lv->X * lv->Y;
-  const size_t smem = static_cast<size_t>(cells) * 40;                 // 4 f64 + 4 u16 per cell
-  const int use_smem = cells <= 16383 && smem <= 200 * 1024;
-  if (use_smem && smem > 48 * 1024) {
+  const int use_wr = max_steps <= kMcMaxStagedT;
+  const size_t wr_bytes = use_wr ? static_cast<size_t>(max_steps) * 16 : 0;   // masked weights + rewards, f64
+  const size_t tab_bytes = static_cast<size_t>(cells) * 40;                   // 4 f64 + 4 u16 per cell
+  const int use_smem = cells <= 16383 && wr_bytes + tab_bytes <= 200 * 1024;
+  const size_t smem = wr_bytes + (use_smem ? tab_bytes : 0);
+  if (smem > 48 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(mc_evaluate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          static_cast<int>(smem));
     if (e != cudaSuccess) return static_cast<int>(e);
   }
-  mc_evaluate_kernel<<<1, kMcThreads, use_smem ? smem : 0, static_cast<cudaStream_t>(stream)>>>(
+  mc_evaluate_kernel<<<1, kMcThreads, smem, static_cast<cudaStream_t>(stream)>>>(
       view_of(lv, 1), cdf, uniforms, n_uniforms, starts, n_episodes, max_steps, weights, keep, every_visit, mode, alpha,
       cells, obs_scratch, rew_scratch, g_scratch, total_visits, total_return, value, lengths, done,
-      reinterpret_cast<long long*>(meta), use_smem);
+      reinterpret_cast<long long*>(meta), use_smem, use_wr);
   GU_CHECK_LAUNCH();
   return GU_OK;
 }

@@ -2,9 +2,10 @@
 
 Same constructor, attributes, return conventions and error behaviour as
 core/envs/griduniverse_env.py:14-321 of the reference; the transition itself
-(`step` / `look_step_ahead`) runs in the batched CUDA kernel with a batch of one, so a
-single call costs one launch + one stream synchronise (results land in pinned host memory).  There is no CPU transition code in
-this class: without a CUDA device `step` raises.  Use ``GridUniverseVecEnv`` for throughput.
+(`step` / `look_step_ahead`) is answered by a resident one-warp CUDA kernel through a pinned
+mailbox (a PCIe round trip per call; `GU_STEP_SERVER=0`: one launch + one stream synchronise per
+call).  There is no CPU transition code in this class: without a CUDA device `step` raises.
+Use ``GridUniverseVecEnv`` for throughput.
 
 Not carried over: the pyglet window (`render(mode='graphic')`) -- GUI, out of scope (SURVEY 2,
 rows 7-8).  What the viewer draws is available headless: `render(mode='rgb_array')` and
@@ -22,6 +23,85 @@ from six import StringIO
 from .. import _cabi
 from ..level import Level, parse_level_text, read_level_file
 from ..spaces import Discrete
+
+
+_SERVER_ON = __import__("os").environ.get("GU_STEP_SERVER", "1") != "0"
+
+
+class _LookServer(object):
+    """Host side of the resident look_step_ahead service (gu_look_server_start, include/gu_b200.h).
+
+    One pinned 128-byte mailbox: ``look`` writes the request as a single 8-byte store, spins on the
+    answer's sequence number and (re)launches the one-warp kernel whenever the mailbox says it has
+    left (it leaves after ~1 ms without requests, so device-wide synchronisation is never held up
+    for long).  A call that gets no answer within ``timeout_s`` raises instead of spinning forever."""
+
+    IDLE_CYCLES = 2000000          # ~1 ms of SM clock without a request: the kernel leaves
+    MAX_CYCLES = 40000000000       # ~20 s: upper bound on one residency
+
+    def __init__(self, vec, timeout_s=10.0):
+        import torch
+        self._torch = torch
+        self.vec = vec
+        self.lib = vec._lib
+        self.timeout_s = float(timeout_s)
+        raw = torch.zeros(64 + 32, dtype=torch.int32).pin_memory()     # room to align to 128 bytes
+        off = (-raw.data_ptr() % 128) // 4
+        self._raw = raw
+        self.mail = raw[off:off + 32]
+        m = self.mail.numpy()
+        self.req = m[0:2].view(np.uint64)
+        self.ack = m[16:20].view(np.uint32)
+        self.ack_i = m[16:20]
+        self.alive = m[20:21]
+        self.seq = 0
+        self.ptr = ctypes.c_void_p(self.mail.data_ptr())
+        with torch.cuda.device(vec.device):
+            self.stream = torch.cuda.Stream(vec.device)
+
+    def _launch(self, answered):
+        self.alive[0] = 1
+        with self._torch.cuda.device(self.vec.device):
+            rc = self.lib.gu_look_server_start(self.vec.levels.ref(), self.ptr, answered, self.IDLE_CYCLES,
+                                               self.MAX_CYCLES, ctypes.c_void_p(self.stream.cuda_stream))
+        if rc:
+            self.alive[0] = 0
+        _cabi.check("gu_look_server_start", rc)
+
+    def look(self, state, action, care_about_terminal=True):
+        import time
+        prev = self.seq
+        seq = self.seq = (prev % 0x7fffffff) + 1
+        word = seq | ((action & 3) | (0 if care_about_terminal else 4) | (int(state) << 3)) << 32
+        self.req[0] = word
+        ack, alive = self.ack, self.alive
+        if not alive[0]:
+            self._launch(prev)
+        if ack[0] != seq:
+            deadline = None
+            spins = 0
+            while ack[0] != seq:
+                if not alive[0] and ack[0] != seq:
+                    self._launch(prev)               # it left before it saw this request
+                spins += 1
+                if spins & 0x3ff == 0:
+                    now = time.monotonic()
+                    if deadline is None:
+                        deadline = now + self.timeout_s
+                    elif now > deadline:
+                        raise RuntimeError("look_step_ahead service did not answer within %.0f s" % self.timeout_s)
+        a = self.ack_i
+        return int(a[1]), np.int64(a[2]), bool(a[3])
+
+    def close(self):
+        """Wait for the kernel to leave (it does so by itself after the idle interval): the mailbox and
+        the level's planes must not be released under a resident kernel."""
+        try:
+            self.stream.synchronize()
+        except Exception:                                # noqa: BLE001 - interpreter shutdown
+            pass
+
+    __del__ = close
 
 
 class GridUniverseEnv(object):
@@ -76,6 +156,9 @@ class GridUniverseEnv(object):
         self.wall_grid = level.wall.astype(np.float64)
         self.reward_matrix = level.rewards()
         self._vec = None   # device state is rebuilt lazily for the new level
+        if getattr(self, "_look_server", None) is not None:
+            self._look_server.close()
+        self._look_server = None
 
     @classmethod
     def from_text_lines(cls, lines, device="cuda"):
@@ -103,13 +186,23 @@ class GridUniverseEnv(object):
         return self._vec
 
     # ------------------------------------------------------------------ reference API
+    def _server(self):
+        if self._look_server is None:
+            self._look_server = _LookServer(self._device_env())
+        return self._look_server
+
     def look_step_ahead(self, state, action, care_about_terminal=True):
         """griduniverse_env.py:136-155 -> (next_state, reward, is_terminal)."""
         if not -4 <= action <= 3:
             raise IndexError("list index out of range")
         if not 0 <= state < self.world.size:
             raise IndexError("index {} is out of bounds for axis 0 with size {}".format(state, self.world.size))
-        # scalar fast path: the kernel reads (state, action) from and writes (next, reward, terminal)
+        # resident service (gu_look_server_start): the request and the answer cross PCIe through a pinned
+        # mailbox while a one-warp kernel stays resident -- a few microseconds per call instead of a
+        # launch and a stream synchronise.  GU_STEP_SERVER=0 selects the launch-per-call path below.
+        if _SERVER_ON and self.world.size <= (1 << 29):
+            return self._server().look(state, action, care_about_terminal)
+        # scalar path: the kernel reads (state, action) from and writes (next, reward, terminal)
         # to one pinned host buffer directly (pinned memory is device-addressable under unified
         # addressing), so a step is one launch and one stream synchronise -- no staging copies
         vec = self._device_env()

@@ -159,6 +159,18 @@ int64_t gu_tables_bytes(const gu_levels* lv, int64_t n_envs);
  * (cell, action) as uint16. */
 int gu_pack_tables(const gu_levels* lv, int64_t n_envs, uint32_t* tables, uint32_t flags, void* stream);
 
+/* Resident look_step_ahead service for a one-env step loop (griduniverse_env.py:176-185): launches a
+ * one-warp kernel that answers (state, action) requests written into `mailbox` -- 32 x uint32, 128-byte
+ * aligned, pinned host memory -- until `idle_cycles` SM cycles pass without a request or `max_cycles`
+ * since the launch, then clears the alive word and leaves (relaunch on demand).  Shared level only.
+ *   mailbox[0:2]   request, ONE 8-byte host store: bits 0-31 sequence number (any value different from
+ *                  the previous request's; `seq0` = the last one already answered), 32-33 action,
+ *                  34 = care_about_terminal is False, 35-63 state
+ *   mailbox[16:20] answer, one 16-byte device store: {sequence number, next state, reward, terminal}
+ *   mailbox[20]    alive: the host sets it to 1 before calling, the kernel clears it when it leaves */
+int gu_look_server_start(const gu_levels* lv, void* mailbox, uint32_t seq0, int64_t idle_cycles,
+                         int64_t max_cycles, void* stream);
+
 /* look_step_ahead for M arbitrary (state, action) pairs (griduniverse_env.py:136-155).
  * Shared level: any M.  per_env levels: pair i is evaluated on level i (M == N).
  *   states int32[M], actions int32[M] -> next int32[M], reward int32[M], terminal uint8[M] */

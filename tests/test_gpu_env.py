@@ -315,3 +315,34 @@ def test_look_step_ahead_per_env_levels(shape, n):
         assert np.array_equal(nxt, [e[0] for e in exp])
         assert np.array_equal(rew, [e[1] for e in exp])
         assert np.array_equal(np.asarray(term).astype(bool), [e[2] for e in exp])
+
+
+def test_look_server_equals_launch_per_call_and_relaunches(golden_levels):
+    """The resident look_step_ahead service (gu_look_server_start) answers exactly what the launch-per-call
+    path answers, for every (state, action) of a shipped level and both terminal modes, and comes back
+    after it has left (idle interval ~1 ms)."""
+    import time
+    from griduniverse_b200.envs import griduniverse_env as ge
+    env = GridUniverseEnv.from_text_lines(golden_levels["maze_21x21"])
+    N = env.world.size
+    assert ge._SERVER_ON
+    served = [env.look_step_ahead(s, a, care) for care in (True, False) for s in range(N) for a in range(-4, 4)]
+    assert env._look_server is not None and env._look_server.seq == len(served)
+    ge._SERVER_ON = False
+    try:
+        launched = [env.look_step_ahead(s, a, care) for care in (True, False) for s in range(0, N, 7) for a in range(-4, 4)]
+    finally:
+        ge._SERVER_ON = True
+    pick = [served[(c * N + s) * 8 + (a + 4)] for c in (0, 1) for s in range(0, N, 7) for a in range(-4, 4)]
+    assert pick == launched
+    time.sleep(0.02)                                  # the kernel has left by now
+    torch.cuda.synchronize()                          # and a device-wide sync returns
+    assert int(env._look_server.alive[0]) == 0
+    assert env.look_step_ahead(0, 1) == served[0 * 8 + 5]
+    time.sleep(0.02)
+    o, r, d, _ = env.step(2)
+    assert isinstance(d, bool) and 0 <= o < N
+    # a new level on the same env object gets a new service
+    env._create_custom_world_from_text(orc.strip_level_lines(golden_levels["maze_11x11"]))
+    assert env._look_server is None
+    assert env.look_step_ahead(env.current_state, 0)[0] in range(env.world.size)
