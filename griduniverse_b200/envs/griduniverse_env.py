@@ -16,6 +16,7 @@ depth-first maze carver, so a given `random.seed` does not reproduce the referen
 import ctypes
 import random
 import sys
+import time
 
 import numpy as np
 from six import StringIO
@@ -69,7 +70,6 @@ class _LookServer(object):
         _cabi.check("gu_look_server_start", rc)
 
     def look(self, state, action, care_about_terminal=True):
-        import time
         prev = self.seq
         seq = self.seq = (prev % 0x7fffffff) + 1
         word = seq | ((action & 3) | (0 if care_about_terminal else 4) | (int(state) << 3)) << 32
