@@ -62,6 +62,9 @@ def step():
 
 
 row("step, one per launch (29 B/step)", timeit(step, n=20), 29.0 * n)
+# the same launch by the bytes it really moves for 8x8 levels: two words per plane (24 B of masks, not 12),
+# position read AND written -- 32 B in, 13 B out per env step (ncu: 0.570 GB read + 0.190 GB written)
+row("  ... by the 45 B/step it moves (2 words per plane)", timeit(step, n=20), 45.0 * n)
 packed, _ = env.pack_actions(acts)
 row("rollout, packed 2-bit actions (0.25 B/step), T=32", timeit(lambda: env.rollout(packed, per_env=True, packed_steps=T), n=10),
     0.25 * n * T)
