@@ -4,7 +4,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-for rows in (2048, 4096):
+for rows in [int(r) for r in os.environ.get('SCAN_ROWS', '2048,4096').split(',')]:
     for rpb in (0, 28, 32, 38, 44, 48, 56, 64, 76, 86, 96, 128):
         env = dict(os.environ, ROWS=str(rows), ONLY="f32")
         if rpb:
