@@ -154,6 +154,9 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
 #ifndef GU_F32_PACK_FOLD
 #define GU_F32_PACK_FOLD 1      // acc = fma(w, p*g, acc): exact for w in {0, 1}, one packed op instead of two
 #endif
+#ifndef GU_F32_DENORM_IDX
+#define GU_F32_DENORM_IDX 1     // tie count + table offset accumulated as a denormal (its bits ARE the byte offset)
+#endif
 #ifndef GU_F32_PACK_W
 #define GU_F32_PACK_W 0         // 1: tie weights on the FMA pipe (max(ra - m + 1, 0)) instead of FSET
 #endif
@@ -185,12 +188,24 @@ __device__ __forceinline__ void backup_ties_pair(const float (&ra0)[4], const fl
     asm("set.eq.f32.f32 %0, %1, %2;" : "=f"(w[a].y) : "f"(ra1[a]), "f"(m1));
   }
 #endif
+#if GU_F32_DENORM_IDX
+  // The table offset is accumulated as a DENORMAL: a denormal's bit pattern is its value in units of
+  // 2^-149, so starting from the cell's goal / lava offset and adding 32 * 2^-149 per tie leaves the byte
+  // offset of the {1/len(ties), R} entry in the register as it is -- no mask, no OR (sums of denormals
+  // below 2^-126 are exact, and FFMA2 handles denormals at full rate without .ftz).
+  float2 c = make_float2(__uint_as_float(off0), __uint_as_float(off1));
+  const float2 k32 = make_float2(__uint_as_float(32u), __uint_as_float(32u));
+#pragma unroll
+  for (int a = 0; a < 4; ++a) c = __ffma2_rn(w[a], k32, c);
+  const uint32_t i0 = __float_as_uint(c.x), i1 = __float_as_uint(c.y);
+#else
   // count of ties in mantissa bits 5-7 of a magic-number sum
   float2 c = make_float2(8388608.0f, 8388608.0f);
   const float2 k32 = make_float2(32.0f, 32.0f);
 #pragma unroll
   for (int a = 0; a < 4; ++a) c = __ffma2_rn(w[a], k32, c);
   const uint32_t i0 = (__float_as_uint(c.x) & 0xe0u) | off0, i1 = (__float_as_uint(c.y) & 0xe0u) | off1;
+#endif
   const float2 p = make_float2(lds_f32(&l.prs[0][0], i0), lds_f32(&l.prs[0][0], i1));
   float2 acc = make_float2(lds_f32(&l.prs[0][1], i0), lds_f32(&l.prs[0][1], i1));      // R[s]
 #pragma unroll
