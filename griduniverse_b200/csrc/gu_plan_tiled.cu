@@ -106,10 +106,49 @@ __device__ __forceinline__ float backup_ties(float rs, const float (&ra)[4], flo
 }
 // f64: the four compares feed predicated mul / add pairs (PTX).  A/B on B200 at 16384^2:
 // 1.38 ms this way, 1.42 ms with C++ selects, 1.54 ms with 0/1 weight multiplies.
+// GU_F64_FMA_W: the compare selects a 0.0 / 1.0 weight (one SEL on the high word) and the term goes in as
+// acc = fma(w, p * g, acc) -- exact for w in {0, 1}: fma(1, x, acc) rounds acc + x once like the add, and
+// fma(0, x, acc) is acc -- instead of a predicated add, which costs a DADD and two 32-bit selects.
+#ifndef GU_F64_FMA_W
+#define GU_F64_FMA_W 1
+#endif
 __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], double m, const double (&ga)[4],
                                               const Luts<double>& l) {
   double acc;
   const uint32_t lut = static_cast<uint32_t>(__cvta_generic_to_shared(&l.inv_cnt[0]));
+#if GU_F64_FMA_W
+  asm("{\n\t"
+      ".reg .pred t0, t1, t2, t3;\n\t"
+      ".reg .u32 c, a;\n\t"
+      ".reg .f64 p, x, w;\n\t"
+      "setp.eq.f64 t0, %2, %6;\n\t"
+      "setp.eq.f64 t1, %3, %6;\n\t"
+      "setp.eq.f64 t2, %4, %6;\n\t"
+      "setp.eq.f64 t3, %5, %6;\n\t"
+      "mov.u32 c, 0;\n\t"
+      "@t0 add.u32 c, c, 8;\n\t"
+      "@t1 add.u32 c, c, 8;\n\t"
+      "@t2 add.u32 c, c, 8;\n\t"
+      "@t3 add.u32 c, c, 8;\n\t"
+      "add.u32 a, c, %11;\n\t"
+      "ld.shared.f64 p, [a];\n\t"
+      "mul.rn.f64 x, p, %7;\n\t"
+      "selp.f64 w, 0d3FF0000000000000, 0d0000000000000000, t0;\n\t"
+      "fma.rn.f64 %0, w, x, %1;\n\t"
+      "mul.rn.f64 x, p, %8;\n\t"
+      "selp.f64 w, 0d3FF0000000000000, 0d0000000000000000, t1;\n\t"
+      "fma.rn.f64 %0, w, x, %0;\n\t"
+      "mul.rn.f64 x, p, %9;\n\t"
+      "selp.f64 w, 0d3FF0000000000000, 0d0000000000000000, t2;\n\t"
+      "fma.rn.f64 %0, w, x, %0;\n\t"
+      "mul.rn.f64 x, p, %10;\n\t"
+      "selp.f64 w, 0d3FF0000000000000, 0d0000000000000000, t3;\n\t"
+      "fma.rn.f64 %0, w, x, %0;\n\t"
+      "}"
+      : "=&d"(acc)
+      : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
+        "d"(ga[3]), "r"(lut));
+#else
   asm("{\n\t"
       ".reg .pred t0, t1, t2, t3;\n\t"
       ".reg .u32 c, a;\n\t"
@@ -138,6 +177,7 @@ __device__ __forceinline__ double backup_ties(double rs, const double (&ra)[4], 
       : "=&d"(acc)
       : "d"(rs), "d"(ra[0]), "d"(ra[1]), "d"(ra[2]), "d"(ra[3]), "d"(m), "d"(ga[0]), "d"(ga[1]), "d"(ga[2]),
         "d"(ga[3]), "r"(lut));
+#endif
   return acc;
 }
 
