@@ -630,8 +630,12 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
   const char* pf_base = nullptr;
   if (lane < kVLines) pf_base = reinterpret_cast<const char*>(vin + wx0) + lane * 128;
   else if (lane < kVLines + kILines) pf_base = reinterpret_cast<const char*>(info + wx0) + (lane - kVLines) * 128;
+  else if (KIND == GU_POLICY_MASK && !WRITE_TIE && lane < kVLines + 2 * kILines)      // the tie-mask plane, same geometry as info
+    pf_base = static_cast<const char*>(policy) + wx0 + (lane - kVLines - kILines) * 128;
   const int pf_pitch = lane < kVLines ? pitch * static_cast<int>(sizeof(T)) : pitch;   // bytes; prefetch only
-  const bool pf_on = pf_base != nullptr && wx0 + (lane < kVLines ? lane * (128 / static_cast<int>(sizeof(T))) : (lane - kVLines) * 128) < g.pitch;
+  const int pf_col = lane < kVLines ? lane * (128 / static_cast<int>(sizeof(T)))
+                                    : (lane < kVLines + kILines ? lane - kVLines : lane - kVLines - kILines) * 128;
+  const bool pf_on = pf_base != nullptr && wx0 + pf_col < g.pitch;
 
   // ---- TMA ring (TMA = true): per-warp state -------------------------------------------------------
   extern __shared__ __align__(1024) uint8_t ring_raw[];
@@ -823,6 +827,24 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
 
   T dmax = N::neg_inf();
   const int last_ar = rows + 1;                 // bottom ghost row of the shard's arrays
+  // GU_POLICY_MASK: the row's tie masks are loaded one row of compute ahead, like the window (loaded at
+  // the point of use they were the kernel's exposed latency: long-scoreboard stalls of 5 per issue)
+  uint32_t pm_next[IW];
+#pragma unroll
+  for (int k = 0; k < IW; ++k) pm_next[k] = 0;
+  auto load_masks = [&](int ar) {               // masks of array row `ar` (an owned row)
+    if constexpr (KIND == GU_POLICY_MASK && !WRITE_TIE) {
+      if (active) {
+        const uint8_t* pp = static_cast<const uint8_t*>(policy) + ar * pitch + x0;
+        if (CPT == 2) pm_next[0] = *reinterpret_cast<const uint16_t*>(pp);
+        else {
+#pragma unroll
+          for (int k = 0; k < IW; ++k) pm_next[k] = *reinterpret_cast<const uint32_t*>(pp + 4 * k);
+        }
+      }
+    }
+  };
+  load_masks(ry0 + 1);
   issue_loads(ry0, w[0]);                       // array row ry0     = row above the first owned row
   issue_loads(ry0 + 1, w[1]);                   // array row ry0 + 1 = first owned row
   issue_loads(ry0 + 2, w[2]);
@@ -856,15 +878,8 @@ sweep_tiled_kernel(GridView g, const uint8_t* __restrict__ info, const T* __rest
           uint32_t ties[IW];
           uint32_t pm[IW];
 #pragma unroll
-          for (int k = 0; k < IW; ++k) { ties[k] = 0; pm[k] = 0; }
-          if (KIND == GU_POLICY_MASK) {
-            const uint8_t* pp = static_cast<const uint8_t*>(policy) + o;
-            if (CPT == 2) pm[0] = *reinterpret_cast<const uint16_t*>(pp);
-            else {
-#pragma unroll
-              for (int k = 0; k < IW; ++k) pm[k] = *reinterpret_cast<const uint32_t*>(pp + 4 * k);
-            }
-          }
+          for (int k = 0; k < IW; ++k) { ties[k] = 0; pm[k] = pm_next[k]; }
+          if (ry + 1 < ry1) load_masks(ry + 2);          // next row's masks: in flight while this row is computed
           if constexpr (WRITE_TIE && GU_TIE_FMA) {
             // Greedy extraction: the kernel is bound by the half-rate ALU pipe (selects, compares, bit
             // assembly), so the tie mask is assembled on the FMA pipe instead: every tie adds 2^(a + 8 j)
