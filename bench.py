@@ -674,31 +674,35 @@ def run_profile(args):
     from griduniverse_b200.planner import Planner
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(0)
+    only_sweeps = os.environ.get("GU_PROFILE_ONLY") == "sweep"     # re-capture of the sweep kernels alone
     n = ENV_TOTAL // args.profile_div
-    levels = synth.env_levels_device(ENV_SHAPE[0], ENV_SHAPE[1], n, seed=0, device=dev)
-    env = GridUniverseVecEnv(n, levels=levels, auto_reset=True, device=dev)
-    actions = torch.randint(0, 4, (ENV_T, n), dtype=torch.int32, device=dev)
-    for _ in range(2):
-        env.rollout(actions, trajectories=False, per_env=True)
-    packed, _ = env.pack_actions(actions)
-    env.rollout(packed, trajectories=False, per_env=True, packed_steps=ENV_T)
-    env.step(actions[0])
-    del actions, packed, env, levels
-    # cfg 3: 65,536 16x16 envs, T = 1024 (one env per lane, 4-stage ring)
-    lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
-    env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
-    a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev)
-    env3.rollout(a3, per_env=True)
-    del a3, env3, lv3
-    # cfg 2 in batch form: 4,736 10x10 mazes, one block each
-    from griduniverse_b200.batch import MazeBatch
-    from griduniverse_b200.envs import GridUniverseEnv
-    with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:
-        lv10 = json.load(f)
-    base = [GridUniverseEnv.from_text_lines(lv10["gen10_%d" % k]).level for k in range(10)]
-    mb = MazeBatch([base[i % 10] for i in range(148 * 32)], device=dev)
-    mb.value_iteration("uniform", None, 1e-6, 1000, 0.9)
-    mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9)
+    if only_sweeps:
+        n = 0
+    if not only_sweeps:
+        levels = synth.env_levels_device(ENV_SHAPE[0], ENV_SHAPE[1], n, seed=0, device=dev)
+        env = GridUniverseVecEnv(n, levels=levels, auto_reset=True, device=dev)
+        actions = torch.randint(0, 4, (ENV_T, n), dtype=torch.int32, device=dev)
+        for _ in range(2):
+            env.rollout(actions, trajectories=False, per_env=True)
+        packed, _ = env.pack_actions(actions)
+        env.rollout(packed, trajectories=False, per_env=True, packed_steps=ENV_T)
+        env.step(actions[0])
+        del actions, packed, env, levels
+        # cfg 3: 65,536 16x16 envs, T = 1024 (one env per lane, 4-stage ring)
+        lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
+        env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
+        a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev)
+        env3.rollout(a3, per_env=True)
+        del a3, env3, lv3
+        # cfg 2 in batch form: 4,736 10x10 mazes, one block each
+        from griduniverse_b200.batch import MazeBatch
+        from griduniverse_b200.envs import GridUniverseEnv
+        with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:
+            lv10 = json.load(f)
+        base = [GridUniverseEnv.from_text_lines(lv10["gen10_%d" % k]).level for k in range(10)]
+        mb = MazeBatch([base[i % 10] for i in range(148 * 32)], device=dev)
+        mb.value_iteration("uniform", None, 1e-6, 1000, 0.9)
+        mb.policy_iteration("uniform", None, 1e-6, 1000, 0.9)
     size = VI_SIZE // max(1, int(args.profile_div ** 0.5) // 2 * 2 or 1)
     for dt in (np.float32, np.float64):
         grid = synth.maze_plan_grid(size, size, seed=0, dtype=dt, device=dev)
@@ -710,7 +714,7 @@ def run_profile(args):
             pl.sweep(b if i % 2 == 0 else a, a if i % 2 == 0 else b, 3, None, VI_GAMMA, res[i + 1:i + 2])
         tie = pl.greedy(a, VI_GAMMA)
         pl.sweep(a, b, 1, tie, VI_GAMMA)
-        if dt == np.float32:                 # eight levels of the shortest-path wavefront
+        if dt == np.float32 and not only_sweeps:                 # eight levels of the shortest-path wavefront
             from griduniverse_b200.paths import ShortestPaths
             ShortestPaths(grid, chunk=8).solve(None, lava_blocks=True, max_levels=8)
         del a, b, tie, pl, grid

@@ -62,6 +62,9 @@ with open(tpath, "w") as f:
     json.dump(traffic, f, indent=1)
 # launch list: keep kernel name, grid, block, time
 src = os.path.join(ROOT, "gpurun_out", tag + "_launches.csv")
+if not os.path.exists(src):          # a re-capture of some kernels only: no launch list of its own
+    print("traffic", traffic)
+    sys.exit(0)
 lines = [l for l in open(src) if l.startswith('"')]
 rd = list(csv.reader(lines))
 h = rd[0]
