@@ -60,6 +60,13 @@ class _LookServer(object):
         with torch.cuda.device(vec.device):
             self.stream = torch.cuda.Stream(vec.device)
 
+    @staticmethod
+    def request_word(seq, state, action, care_about_terminal=True):
+        """The 8-byte request of include/gu_b200.h (gu_look_server_start): bits 0-31 sequence number,
+        32-33 action (two low bits: -1 is LEFT like the reference's list index), 34 = do not care about
+        terminals, 35-63 state."""
+        return seq | ((action & 3) | (0 if care_about_terminal else 4) | (int(state) << 3)) << 32
+
     def _launch(self, answered):
         self.alive[0] = 1
         with self._torch.cuda.device(self.vec.device):
@@ -72,8 +79,7 @@ class _LookServer(object):
     def look(self, state, action, care_about_terminal=True):
         prev = self.seq
         seq = self.seq = (prev % 0x7fffffff) + 1
-        word = seq | ((action & 3) | (0 if care_about_terminal else 4) | (int(state) << 3)) << 32
-        self.req[0] = word
+        self.req[0] = self.request_word(seq, state, action, care_about_terminal)
         ack, alive = self.ack, self.alive
         if not alive[0]:
             self._launch(prev)

@@ -222,3 +222,23 @@ def test_bench_reference_arm_prints_one_json_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["sample"] and cb["value"] == line["value"]
     assert line["e2e"] == {"value": line["value"], "unit": line["unit"], "h2d_bytes_per_step": 0,
                            "d2h_bytes_per_step": 0}
+
+
+def test_look_server_request_word_layout():
+    """Host side of the resident look_step_ahead service: the request word's bit layout is the one
+    include/gu_b200.h documents (the kernel decodes seq = low word, hi & 3 = action, hi & 4 = no-care,
+    hi >> 3 = state)."""
+    from griduniverse_b200.envs.griduniverse_env import _LookServer
+    for seq, state, action, care in ((1, 0, 0, True), (7, 5, 3, True), (0x7fffffff, (1 << 29) - 1, -1, False),
+                                     (12345, 440, -4, False), (2, 99, 2, True)):
+        w = _LookServer.request_word(seq, state, action, care)
+        assert 0 <= w < (1 << 64)
+        lo, hi = w & 0xffffffff, w >> 32
+        assert lo == seq
+        assert hi & 3 == action % 4                    # -1 -> LEFT (3), -4 -> UP (0)
+        assert bool(hi & 4) == (not care)
+        assert hi >> 3 == state
+    # the header documents the same layout
+    import os
+    text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gu_b200.h")).read()
+    assert "gu_look_server_start" in text and "32-33 action" in text and "35-63 state" in text
