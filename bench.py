@@ -155,6 +155,17 @@ def run_reference(args):
     emit(line)
 
 
+def guarded(name, fn):
+    """Run an auxiliary, rank-0-only section of the bench (no collectives inside): a failure there is
+    reported in its own object and on stderr instead of taking the headline line down with it."""
+    try:
+        return fn()
+    except Exception as e:      # noqa: BLE001
+        import traceback
+        sys.stderr.write("bench section %s failed:\n%s\n" % (name, traceback.format_exc()))
+        return {"error": "%s: %r" % (name, e)}
+
+
 def env_config(n_gpus):
     return {"workload": "cfg4: 16,777,216 independent 8x8 envs (per-env walls/lava/goal bit planes), "
                         "T=256 int32 actions per env per pass, auto-reset, summaries only",
@@ -285,7 +296,8 @@ def run_ours(args):
 
     # ------------------------------------------------------------------ cfg 3 (rank 0, extra)
     cfg3 = None
-    if rank == 0:
+
+    def run_cfg3():
         lv3 = synth.env_levels_device(CFG3_SHAPE[0], CFG3_SHAPE[1], CFG3_N, seed=0, device=dev)
         env3 = GridUniverseVecEnv(CFG3_N, levels=lv3, auto_reset=True, device=dev)
         a3 = torch.randint(0, 4, (CFG3_T, CFG3_N), dtype=torch.int32, device=dev, generator=gen)
@@ -303,12 +315,16 @@ def run_ours(args):
         e1.record()
         torch.cuda.synchronize()
         t3 = e0.elapsed_time(e1) / 1000.0 / K3
-        cfg3 = {"workload": "cfg3: 65,536 16x16 envs, T=1024, per-env levels, 1 GPU; inputs larger than L2 (268 MB of "
+        out3 = {"workload": "cfg3: 65,536 16x16 envs, T=1024, per-env levels, 1 GPU; inputs larger than L2 (268 MB of "
                             "actions per pass), %d launches back to back" % K3,
                 "value": CFG3_N * CFG3_T / t3, "unit": "steps/s", "ms_per_pass": 1000 * t3,
                 "roofline_frac": BYTES_PER_STEP_SUMMARY * CFG3_N * CFG3_T / t3 / 1e9 / peak}
         del env3, a3, lv3
         torch.cuda.empty_cache()
+        return out3
+
+    if rank == 0:
+        cfg3 = guarded("cfg3", run_cfg3)
 
     # ------------------------------------------------------------------ VI workload (cfg 5)
     r0, r1 = shard_rows(VI_SIZE, world, rank)
@@ -461,19 +477,28 @@ def run_ours(args):
     # ------------------------------------------------------------------ small configurations (rank 0)
     cfg1 = cfg2 = None
     if rank == 0:
-        cfg1, cfg2 = small_configs(dev, world)
+        small = guarded("cfg1/cfg2", lambda: small_configs(dev, world))
+        cfg1, cfg2 = small if isinstance(small, tuple) else (small, small)
 
     # ------------------------------------------------------------------ CPU baseline (rank 0, N=1)
     cpu_env = cpu_vi = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    def run_cpu_baseline():
         from oracle import cpu_baseline as cb
         procs = os.cpu_count() or 1
         r = cb.env_steps_per_sec(ENV_SHAPE[0], ENV_SHAPE[1], 32768, 64, procs)
         cpu_env = {"value": r["value"], "unit": "steps/s", "cores": procs, "kind": "port",
-                   "sample": "%d procs x 32768 8x8 envs x 64 steps, oracle NumPy port, same generator" % procs}
+                   "sample": "%d procs x 32768 8x8 envs x 64 steps, oracle NumPy port, same generator" % procs,
+                   # the UNMODIFIED reference on the same env shape, one env per core (SURVEY 8d ii): live when its
+                   # tree is on this box, else the committed authoring-container number (see `where`)
+                   "unmodified_reference": unmodified_reference_env_rate()}
         r = cb.vi_cell_updates_per_sec(512, 512, 4, procs, dtype=np.float32)
         cpu_vi = {"value": r["value"], "unit": "cell-updates/s", "cores": procs, "kind": "port",
                   "sample": "%d replicas of a 512x512 synthetic maze x 4 sweep+greedy iterations, fp32 oracle" % procs}
+        return cpu_env, cpu_vi
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        base = guarded("cpu_baseline", run_cpu_baseline)
+        cpu_env, cpu_vi = base if isinstance(base, tuple) else (base, base)
 
     if rank == 0:
         line = {
@@ -529,9 +554,20 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_REF_CPU = None
+
+
 def reference_cpu_numbers():
     """The UNMODIFIED reference timed on this box's host cores when its tree is present
-    (oracle/ref_timing.py), else the committed numbers from the authoring container, labelled."""
+    (oracle/ref_timing.py), else the committed numbers from the authoring container, labelled.
+    Measured once per run."""
+    global _REF_CPU
+    if _REF_CPU is None:
+        _REF_CPU = _reference_cpu_numbers()
+    return _REF_CPU
+
+
+def _reference_cpu_numbers():
     try:
         from oracle import ref_timing
         if ref_timing.available():
@@ -548,6 +584,14 @@ def reference_cpu_numbers():
                       "tree does not exist on the GPU box")
         return r
     return {"unavailable": "no reference tree on this box and no committed timing"}
+
+
+def unmodified_reference_env_rate():
+    """{steps_per_s, cores, sample, where} of the unmodified reference stepping the cfg-4 env shape."""
+    ref = reference_cpu_numbers()
+    out = dict(ref.get("cfg4_shape") or {"unavailable": ref.get("unavailable", "not measured")})
+    out["where"] = ref.get("where")
+    return out
 
 
 def small_configs(dev, world):

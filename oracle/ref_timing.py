@@ -5,6 +5,7 @@ container: /root/reference; a box where the driver put it under baseline/_ref). 
 GPU box (a Python reference cannot travel), where only the oracle port is timed; the numbers measured
 here are committed under profiles/ (SURVEY section 8d items i, iii, iv)."""
 import json
+import multiprocessing as mp
 import os
 import time
 import warnings
@@ -20,8 +21,46 @@ def available():
     return ref_shim.reference_available()
 
 
+def _ref_env_worker(args):
+    """One process: the unmodified reference env on synthetic level `index` of the cfg-3 / cfg-4 generator
+    (walls / lava / goal), `steps` host-supplied random actions, reset on done
+    (griduniverse_env.py:176-193; the caller's loop of examples/griduniverse_env_examples.py:15,22-24)."""
+    X, Y, index, steps, seed = args
+    from griduniverse_b200 import synth     # level synthesis only (input generation, not the hot path)
+    ref = ref_shim.load()
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, 1, first_env=index, seed=seed)
+    env = ref.GridUniverseEnv(grid_shape=(X, Y), initial_state=int(start[0]),
+                              goal_states=[int(c) for c in np.flatnonzero(goal[0])],
+                              lava_states=[int(c) for c in np.flatnonzero(lava[0])],
+                              walls=[int(c) for c in np.flatnonzero(wall[0])])
+    acts = [int(a) for a in np.random.RandomState(seed + 1 + index).randint(0, 4, steps)]
+    env.reset()
+    t0 = time.perf_counter()
+    for a in acts:
+        _, _, done, _ = env.step(a)
+        if done:
+            env.reset()
+    return time.perf_counter() - t0
+
+
+def env_shape_parallel(X, Y, procs=None, steps=200000, seed=0):
+    """SURVEY 8d CPU baseline (ii): the cfg-3 / cfg-4 env shape stepped by the unmodified reference in
+    `procs` independent processes (one env stream each) -> aggregate steps/s, with P stated."""
+    procs = procs or os.cpu_count() or 1
+    jobs = [(X, Y, i, steps, seed) for i in range(procs)]
+    if procs == 1:
+        times = [_ref_env_worker(jobs[0])]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            times = pool.map(_ref_env_worker, jobs)
+    return {"steps_per_s": procs * steps / max(times), "cores": procs, "us_per_step_per_core": max(times) / steps * 1e6,
+            "sample": "%d processes x 1 env (%dx%d synthetic level with walls / lava / goal, generator seed %d) x %d "
+                      "steps of GridUniverseEnv.step, reset on done" % (procs, X, Y, seed, steps)}
+
+
 def time_reference(cfg2_level_lines=None):
-    """Returns a dict of the reference's own timings on ONE core (its loops are single-threaded)."""
+    """Returns a dict of the reference's own timings: ONE core for cfg 1 / cfg 2 / maze_101x101 (its loops are
+    single-threaded), one env per host core for the batched shapes (`cfg4_shape`, `cfg3_shape`)."""
     ref = ref_shim.load()
     Env = ref.GridUniverseEnv
     out = {"kind": "reference", "cores": 1, "root": ref_shim.REFERENCE_ROOT}
@@ -41,6 +80,9 @@ def time_reference(cfg2_level_lines=None):
         dt = time.perf_counter() - t
         out["cfg1"] = {"us_per_step": dt / (reps * 1000) * 1e6, "steps_per_s": reps * 1000 / dt,
                        "sample": "%d x 1000 steps of GridUniverseEnv().step (griduniverse_env.py:176-185)" % reps}
+        # B2 / SURVEY 8d (ii): the batched shapes, one reference env per host core
+        out["cfg4_shape"] = env_shape_parallel(8, 8)
+        out["cfg3_shape"] = env_shape_parallel(16, 16)
         # B3 / cfg 2: 10x10 generated maze, gamma 0.9, theta 1e-6
         if cfg2_level_lines is None:
             with open(os.path.join(ROOT, "tests", "golden", "levels.json")) as f:

@@ -72,3 +72,38 @@ def test_transitions_and_planning_match_the_live_reference(ref, seed, shape):
                 V_orc, P_orc = getattr(orc, name)(p_orc, level, np.zeros(N), theta, steps, gamma)[:2]
                 assert V_ref.tobytes() == np.asarray(V_orc).tobytes(), (name, gamma)
                 assert np.asarray(P_ref).tobytes() == np.asarray(P_orc).tobytes(), (name, gamma)
+
+
+@pytest.mark.parametrize("shape", [(8, 8), (16, 16)])
+def test_synthetic_env_levels_step_like_the_live_reference(ref, shape):
+    """The bench workloads (cfg 3 / cfg 4): per-env synthetic levels with walls / lava / goal, host-supplied
+    actions, reset on done.  One unmodified reference env per level, stepped action by action, must give
+    the oracle's batched rollout (positions, rewards, done flags) -- the same oracle the CUDA path is
+    compared with at these shapes."""
+    from griduniverse_b200 import synth      # level synthesis only
+    X, Y = shape
+    n, T = 12, 400
+    wall, goal, lava, start = synth.env_levels_numpy(X, Y, n, first_env=5, seed=0)
+    actions = np.random.RandomState(9).randint(0, 4, (T, n)).astype(np.int32)
+    levels = [orc.Level.from_masks(X, Y, wall[i], goal[i], lava[i], [int(start[i])]) for i in range(n)]
+    obs, rew, done, pos = orc.rollout(levels, start, actions, auto_reset=True)
+    for i in range(n):
+        env = ref.GridUniverseEnv(grid_shape=(X, Y), initial_state=int(start[i]),
+                                  goal_states=[int(c) for c in np.flatnonzero(goal[i])],
+                                  lava_states=[int(c) for c in np.flatnonzero(lava[i])],
+                                  walls=[int(c) for c in np.flatnonzero(wall[i])])
+        assert env.reset() == int(start[i])
+        for t in range(T):
+            o, r, d, _ = env.step(int(actions[t, i]))
+            assert (o, int(r), bool(d)) == (int(obs[t, i]), int(rew[t, i]), bool(done[t, i])), (i, t)
+            if d:
+                o = env.reset()                 # the caller's reset on done = the batched auto-reset
+        assert o == int(pos[i])                 # final position (after the reset, if the last step ended an episode)
+    assert done.any()                           # the streams do end episodes, so the reset path is exercised
+
+
+def test_reference_env_shape_timing_runs(ref):
+    """oracle/ref_timing.env_shape_parallel (SURVEY 8d CPU baseline ii): two processes, a short stream."""
+    from oracle import ref_timing
+    r = ref_timing.env_shape_parallel(8, 8, procs=2, steps=2000)
+    assert r["cores"] == 2 and r["steps_per_s"] > 0 and "8x8" in r["sample"]
