@@ -39,6 +39,7 @@ ENV_T = 256
 CFG3_N, CFG3_SHAPE, CFG3_T = 65536, (16, 16), 1024
 VI_SIZE = 16384
 VI_GAMMA, VI_THETA = 0.9, 1e-6
+TINY = False                          # --tiny: the whole script on 1/16 of the envs and a 2048^2 grid (a self-check, never a number)
 BYTES_PER_STEP_SUMMARY = 4.0          # int32 action per env step, summaries only
 BYTES_PER_CELL_FUSED_F32 = 8.375      # read V + write V' + 3 mask bits
 TRAFFIC_NOTE = ("profiled constant: dram__bytes_read.sum + dram__bytes_write.sum of this kernel from the committed "
@@ -167,7 +168,8 @@ def guarded(name, fn):
 
 
 def env_config(n_gpus):
-    return {"workload": "cfg4: 16,777,216 independent 8x8 envs (per-env walls/lava/goal bit planes), "
+    return {"workload": ("" if not TINY else "NOT A BENCH NUMBER (--tiny self-check, %d envs, %d^2 grid) -- " % (ENV_TOTAL, VI_SIZE)) +
+                        "cfg4: 16,777,216 independent 8x8 envs (per-env walls/lava/goal bit planes), "
                         "T=256 int32 actions per env per pass, auto-reset, summaries only",
             "envs_total": ENV_TOTAL, "grid": "8x8", "steps_per_pass": ENV_T, "parallelism": "env-sharded x%d, no collective" % n_gpus,
             "l2": "inputs larger than L2 (%.1f GB of actions per GPU per pass)" % (ENV_TOTAL / n_gpus * ENV_T * 4 / 1e9),
@@ -549,6 +551,8 @@ def run_ours(args):
             "cfg1": cfg1, "cfg2": cfg2,
             "cfg3": cfg3,
         }
+        if TINY:
+            line["tiny"] = True
         emit(line)
     if world > 1:
         dist.destroy_process_group()
@@ -788,12 +792,17 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--vi-comm", default="peer", choices=["peer", "nccl"],
                     help="multi-GPU value iteration: collectives fused over peer memory (default) or NCCL")
+    ap.add_argument("--tiny", action="store_true",
+                    help="self-check of this script: every section at 1/16 of the envs and a 2048^2 grid (one GPU; "
+                         "the line says it is not a bench number)")
     ap.add_argument("--profile", action="store_true", help="short kernel sequence for ncu")
     ap.add_argument("--profile-div", type=int, default=1, help="shrink the profile workloads by this factor")
     args = ap.parse_args()
     # stdout carries exactly one line, the JSON result: everything else that writes to fd 1
     # (NCCL prints its version banner there) is sent to stderr
-    global _RESULT_FD
+    global _RESULT_FD, TINY, ENV_TOTAL, VI_SIZE
+    if args.tiny:
+        TINY, ENV_TOTAL, VI_SIZE = True, ENV_TOTAL // 16, 2048
     sys.stdout.flush()
     _RESULT_FD = os.dup(1)
     os.dup2(2, 1)
