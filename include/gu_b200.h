@@ -94,7 +94,8 @@ int gu_rollout(const gu_levels* lv, int64_t n_envs, int64_t n_steps, const int32
 /* int32 actions [T][N] (two low bits used, like gu_rollout) -> the packed stream of
  * GU_FLAG_PACKED_ACTIONS, uint32[ceil(T/16)][N].  gu_pack_actions: device pointers, enqueued on
  * `stream`.  gu_pack_actions_host: HOST pointers, runs on n_threads CPU threads (0 = all cores) and
- * returns when done -- for callers whose action source is a host int32 array. */
+ * returns when done -- for callers whose action source is a host int32 array.  Full 16-step rows are
+ * packed with AVX2 (run-time check) or SSE2 vector code, 16 envs per iteration. */
 int gu_pack_actions(const int32_t* actions, int64_t n_steps, int64_t n_envs, uint32_t* packed, void* stream);
 int gu_pack_actions_host(const int32_t* actions, int64_t n_steps, int64_t n_envs, uint32_t* packed,
                          int32_t n_threads);

@@ -108,6 +108,29 @@ def test_packers():
     assert not edge[0].any() and not edge[-1].any()
 
 
+@pytest.mark.parametrize("path", ["", "sse2", "scalar"])
+def test_host_action_packer(path, monkeypatch):
+    """gu_pack_actions_host (host code of the C-ABI library, no GPU involved): int32 actions [T, N] -> 2 bits per
+    step, 16 steps per word, [ceil(T/16), N]; two low bits only (-1 = LEFT); ragged T and N, every thread
+    count, the AVX2 / SSE2 / scalar forms."""
+    from griduniverse_b200 import _cabi
+    L = _cabi.lib()
+    if path:
+        monkeypatch.setenv("GU_HOST_PACK", path)
+    rs = np.random.RandomState(0)
+    for T, N in ((16, 1), (16, 7), (16, 15), (16, 16), (16, 17), (32, 100003), (5, 33), (37, 4099), (48, 65541), (1, 1)):
+        a = rs.randint(-4, 4, (T, N)).astype(np.int32)
+        want = np.zeros(((T + 15) // 16, N), np.uint32)
+        for t in range(T):
+            want[t // 16] |= (a[t].astype(np.uint32) & 3) << np.uint32(2 * (t % 16))
+        for threads in (0, 1, 3):
+            out = np.full(want.shape, 0xdeadbeef, np.uint32)
+            assert L.gu_pack_actions_host(a.ctypes.data, T, N, out.ctypes.data, threads) == 0
+            assert np.array_equal(out, want), (T, N, threads)
+    assert L.gu_pack_actions_host(None, 16, 4, None, 0) < 0           # GU_ERR_NULL
+    assert L.gu_pack_actions_host(None, 0, 4, None, 0) == 0            # empty: nothing to do
+
+
 def test_mask_policy_round_trip():
     masks = np.arange(16, dtype=np.uint8)
     pol = masks_to_policy(masks)
