@@ -518,7 +518,10 @@ def run_ours(args):
                                  "bytes is %.2f of the 7.7 TB/s HBM3e figure" % (env_achieved, env_achieved / 7700.0)},
             "e2e": {"value": env_e2e_value, "unit": "steps/s", "h2d_bytes_per_step": e2e_io["h2d"] * world,
                     "d2h_bytes_per_step": e2e_io["d2h"] * world,
-                    "note": "pinned host action slabs [16, N] streamed H2D on a side stream, summaries D2H"},
+                    "h2d_gbs_all_ranks": e2e_io["h2d"] * world * k_e2e / t_env_e2e / 1e9,
+                    "h2d_gbs_per_rank": e2e_io["h2d"] * k_e2e / t_env_e2e / 1e9,
+                    "note": "pinned host action slabs [16, N] streamed H2D on a side stream, summaries D2H; the rate is "
+                            "PCIe's (h2d_gbs_*: the bytes above over the timed region, max over ranks)"},
             "e2e_packed": e2e_packed,
             "gpu_launches": env_launches,
             "cpu_baseline": cpu_env,
