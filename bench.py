@@ -4,16 +4,20 @@
 
     python bench.py --gpus N --steps K --warmup W            (N>1: launched with torchrun)
     python bench.py --impl reference ...                      (oracle port on the host cores)
+    python bench.py --tiny ...                                (self-check of this script, not a number)
 
 Workloads (synthetic levels, random actions):
   * env (headline line): BASELINE cfg 4 -- 16,777,216 independent 8x8 envs with per-env
     walls / lava / goal, T = 256 host-supplied actions per env per pass, envs sharded
     contiguously over the N GPUs with no collective (strong scaling: total fixed).
     One "step" = one pass = ONE rollout-kernel launch per GPU = 2^32 env steps in total.
-  * vi: BASELINE cfg 5 -- value iteration (gamma 0.9, theta 1e-6, uniform policy0, V0 = 0) on a
-    16384 x 16384 synthetic maze, fp32, row-sharded over the N GPUs with NCCL halo exchange and a
-    residual MAX all-reduce per sweep.  One pass = one full solve.
-  * cfg3: 65,536 16x16 envs, T = 1024 (rank 0 only, extra line inside the JSON).
+  * vi / pi: BASELINE cfg 5 -- value iteration and policy iteration (gamma 0.9, theta 1e-6, uniform
+    policy0, V0 = 0) on a 16384 x 16384 synthetic maze, fp32, row-sharded over the N GPUs; halo exchange
+    and residual max fused into the sweep kernel over NVLink peer memory (default) or NCCL send/recv +
+    all-reduce per sweep (--vi-comm nccl).  One pass = one full solve.  At N > 1 every rank also solves
+    the whole grid alone and the sharded result must be bit-identical (vi.parity / pi.parity).
+  * cfg1 / cfg2 / cfg3 (rank 0, objects inside the JSON): one GridUniverseEnv through step(); 10x10
+    value / policy iteration, single and 4,736 mazes per launch; 65,536 16x16 envs, T = 1024.
 
 `value`: inputs resident in HBM.  `e2e`: the same workload through the Python API with HOST
 (pinned) buffers, host<->device copies inside the timed region.
