@@ -58,6 +58,35 @@ def env_shape_parallel(X, Y, procs=None, steps=200000, seed=0):
                       "steps of GridUniverseEnv.step, reset on done" % (procs, X, Y, seed, steps)}
 
 
+def _ref_sweep_worker(fp):
+    """One process: one single_step_policy_evaluation + one greedy_policy_from_value_function of the
+    unmodified reference on the level file `fp` (utils.py:15-27,55-72)."""
+    ref = ref_shim.load()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        env = ref.GridUniverseEnv(custom_world_fp=fp)
+        N = env.world.size
+        P = np.ones([N, 4]) / 4
+        t0 = time.perf_counter()
+        v = ref.utils.single_step_policy_evaluation(P, env, 0.9, np.zeros(N))
+        ref.utils.greedy_policy_from_value_function(P, env, v, 0.9)
+        return time.perf_counter() - t0, N
+
+
+def sweep_replicas_parallel(fp, procs=None):
+    """SURVEY 8d CPU baseline (iv), replica-parallel form: a single sweep is not parallelisable in the
+    reference, so `procs` processes each run the sweep + greedy pair on their own copy of the level."""
+    procs = procs or os.cpu_count() or 1
+    if procs == 1:
+        res = [_ref_sweep_worker(fp)]
+    else:
+        with mp.get_context("fork").Pool(procs) as pool:
+            res = pool.map(_ref_sweep_worker, [fp] * procs)
+    worst, N = max(r[0] for r in res), res[0][1]
+    return {"cell_updates_per_s": procs * N / worst, "cores": procs,
+            "sample": "%d replicas of one sweep + one greedy extraction on %s" % (procs, os.path.basename(fp))}
+
+
 def time_reference(cfg2_level_lines=None):
     """Returns a dict of the reference's own timings: ONE core for cfg 1 / cfg 2 / maze_101x101 (its loops are
     single-threaded), one env per host core for the batched shapes (`cfg4_shape`, `cfg3_shape`)."""
@@ -127,6 +156,7 @@ def time_reference(cfg2_level_lines=None):
             out["maze_101x101"] = {"sweep_us_per_cell": (t1 - t0) / N * 1e6, "greedy_us_per_cell": (t2 - t1) / N * 1e6,
                                    "cell_updates_per_s": N / (t2 - t0),
                                    "sample": "one single_step_policy_evaluation + one greedy_policy_from_value_function"}
+            out["maze_101x101_replicas"] = sweep_replicas_parallel(fp)
     return out
 
 

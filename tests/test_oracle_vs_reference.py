@@ -107,3 +107,12 @@ def test_reference_env_shape_timing_runs(ref):
     from oracle import ref_timing
     r = ref_timing.env_shape_parallel(8, 8, procs=2, steps=2000)
     assert r["cores"] == 2 and r["steps_per_s"] > 0 and "8x8" in r["sample"]
+
+
+def test_reference_sweep_replica_timing_runs(ref, tmp_path):
+    """oracle/ref_timing.sweep_replicas_parallel (SURVEY 8d CPU baseline iv, replica-parallel form)."""
+    from oracle import ref_timing
+    fp = tmp_path / "lvl.txt"
+    fp.write_text("xooo\no#oL\noooG\n")
+    r = ref_timing.sweep_replicas_parallel(str(fp), procs=2)
+    assert r["cores"] == 2 and r["cell_updates_per_s"] > 0
