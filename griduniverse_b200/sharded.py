@@ -29,7 +29,13 @@ from . import _cabi
 
 
 def shard_rows(Y, world, rank):
-    """Contiguous, balanced row blocks: rank r owns [r*Y//world, (r+1)*Y//world)."""
+    """Contiguous, balanced row blocks: rank r owns [r*Y//world, (r+1)*Y//world).
+    Every rank must own at least one row (the kernels reject an empty shard, include/gu_b200.h:
+    struct gu_grid), so a grid of Y rows shards over at most Y ranks."""
+    if not 0 <= rank < world:
+        raise ValueError("rank %d outside a world of %d" % (rank, world))
+    if Y < world:
+        raise ValueError("a grid of %d rows cannot be row-sharded over %d ranks (one row per rank at least)" % (Y, world))
     return (rank * Y) // world, ((rank + 1) * Y) // world
 
 

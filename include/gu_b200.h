@@ -217,6 +217,11 @@ int gu_render_rgb(const gu_levels* lv, int64_t n, const int32_t* pos, const doub
  * grid edges).  The bit planes hold the same rows with `pitch_words` uint32 per
  * row, bit (x & 31) of word (x >> 5); bits at x >= X are zero.
  * pitch >= X.
+ * Limits (GU_ERR_SHAPE otherwise): a shard owns at least one row (row_begin < row_end: a grid of Y rows
+ * shards over at most Y ranks) and its arrays hold at most 65,535 rows (rows + 2 ghost rows); the
+ * layout-agnostic kernels take one block row per grid row, so they too stop at 65,535 rows per call.
+ * Taller grids are split into row shards by the caller -- on one GPU as well: shards are independent
+ * launches joined by their ghost rows (griduniverse_b200/sharded.py).
  * `info` (optional, may be NULL): derived per-cell byte plane built once per level by
  * gu_pack_info, same padded layout as the per-cell arrays: bit0/1/2/5 = UP/RIGHT/DOWN/LEFT is
  * blocked (grid edge | wall at the target | cell terminal), bit 3 goal, bit 4 lava.  With it, and

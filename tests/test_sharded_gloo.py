@@ -233,3 +233,9 @@ def test_partitions_cover_everything():
         assert rows[0][0] == 0 and rows[-1][1] == total
         assert all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
         assert [shard_envs(total, world, r) for r in range(world)] == rows
+        assert all(b > a for a, b in rows)                     # no empty shard
+    with pytest.raises(ValueError):
+        shard_rows(3, 4, 0)                                    # fewer rows than ranks: refused up front
+    with pytest.raises(ValueError):
+        shard_rows(16, 4, 4)
+    assert shard_envs(3, 4, 0) == (0, 0)                       # env ranges may be empty (no kernel is launched for them)
