@@ -275,13 +275,18 @@ def run_ours(args):
     del packed_dev
     pk_ring = [env.pack_actions(r)[0] for r in ring]
     pk_io = {}
+    try:
+        host_cpus = len(os.sched_getaffinity(0))
+    except (AttributeError, OSError):
+        host_cpus = os.cpu_count() or 1
+    pack_threads = max(1, host_cpus // world)        # the ranks of one node share its cores
 
     def packed_pass(pack_inside):
         def gen():
             for i in range(ENV_T // slab_t):
                 j = i % len(ring)
                 if pack_inside:
-                    env.pack_actions(ring[j], out=pk_ring[j])
+                    env.pack_actions(ring[j], threads=pack_threads, out=pk_ring[j])
                 yield pk_ring[j]
         out = env.rollout_stream(gen(), packed_steps=slab_t)
         pk_io["h2d"], pk_io["d2h"] = out["h2d_bytes"], out["d2h_bytes"]
@@ -296,7 +301,7 @@ def run_ours(args):
                   "note": "2-bit actions, 16 steps per word: `value` streams PRE-PACKED pinned host slabs (a caller whose "
                           "action source emits packed words); `incl_host_packing_value` starts from the int32 host slabs of "
                           "`e2e` and packs them on the host cores inside the timed region, which reads the same 17 GB of "
-                          "host memory the int32 path sends over PCIe"}
+                          "host memory the int32 path sends over PCIe (%d packer threads per rank)" % pack_threads}
     del ring, pk_ring, actions
     torch.cuda.empty_cache()
 
