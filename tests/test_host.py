@@ -265,3 +265,24 @@ def test_look_server_request_word_layout():
     import os
     text = open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "gu_b200.h")).read()
     assert "gu_look_server_start" in text and "32-33 action" in text and "35-63 state" in text
+
+
+def test_policy_map_and_argmax_actions(capsys):
+    """Host-side helpers of core/algorithms/utils.py:30-52 (arrow map of a policy, printed row by row, two
+    spaces after every cell; every action with probability > 0 gets its arrow, in action order; all-zero
+    terminal rows stay empty) and of the callers' np.argmax (lowest set bit of the tie mask, 0 for a
+    terminal row: examples/griduniverse_alg_examples.py:76,121)."""
+    from griduniverse_b200.algorithms import utils
+    pol = np.array([[0.25] * 4, [0, 1, 0, 0], [0.5, 0, 0.5, 0], [0, 0, 0, 0], [1 / 3, 1 / 3, 0, 1 / 3], [0, 0, 0.5, 0.5]])
+    amap, probs = utils.get_policy_map(pol, (2, 3))
+    assert list(amap) == [u'↑→↓←', u'→', u'↑↓', u'', u'↑→←', u'↓←'] and amap.dtype == np.dtype('<U4')
+    assert capsys.readouterr().out == u'↑→↓←  →  ↑↓  \n  ↑→←  ↓←  \n\n'
+    assert probs.shape == (2, 3) and probs.dtype.names == ('f0', 'f1', 'f2', 'f3')
+    assert tuple(probs[1, 1]) == (1 / 3, 1 / 3, 0.0, 1 / 3)
+    out = utils.get_policy_map(pol, (2, 3), mode='ansi')
+    assert capsys.readouterr().out == ''                       # 'ansi' prints nothing (StringIO), like the reference
+    assert list(out[0]) == list(amap)
+    masks = policy_to_masks(pol)
+    assert list(masks) == [15, 2, 5, 0, 11, 12]
+    assert list(utils.greedy_actions(masks)) == [int(np.argmax(p)) for p in pol] == [0, 1, 0, 0, 0, 2]
+    assert np.array_equal(utils.reshape_as_griduniverse(np.arange(6), (2, 3)), np.arange(6).reshape(2, 3))
