@@ -278,7 +278,11 @@ class GridUniverseVecEnv(object):
         tensors [t_i, N] (consecutive time slices of the action stream); with ``packed_steps=k`` every
         slab is a packed stream of k steps ([ceil(k/16), N], see ``pack_actions``).  Each slab is copied
         host->device on a side stream into one of two device buffers while the kernel works on
-        the previous slab; per-env returns / done counts accumulate across slabs.  Returns NumPy
+        the previous slab; per-env returns / done counts accumulate across slabs.  The copies are
+        asynchronous, but the host never runs more than one copy ahead: when the iterable is asked for
+        slab i + 1 the copies of all slabs before slab i have finished, so a generator that refills pinned
+        buffers may rewrite any buffer it yielded two or more slabs ago (a ring of three, like
+        bench.py's, is safe).  Returns NumPy
         ``pos``, ``env_return``, ``env_done`` and ``stats`` (device->host through pinned memory)."""
         n = self.num_envs
         main = torch.cuda.current_stream()
@@ -317,6 +321,10 @@ class GridUniverseVecEnv(object):
             _cabi.check("gu_rollout", rc)
             free[b].record(main)
             self.launches = getattr(self, "launches", 0) + 1
+            if i >= 1:
+                # bound the host's run-ahead (see the docstring): copy i - 1 has left its pinned source before
+                # the next slab is requested; copy i is queued behind it, so the copy stream never idles
+                ready[(i - 1) % 2].synchronize()
         out = {}
         for k, v in (("pos", self.pos), ("env_return", env_ret), ("env_done", env_done), ("stats", self.stats)):
             h = self._pin("stream_" + k, tuple(v.shape), v.dtype)
