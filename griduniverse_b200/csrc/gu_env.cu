@@ -349,27 +349,35 @@ static void pack_row16_sse2(const int32_t* in, uint32_t* out, int64_t N, int64_t
 }
 #endif
 
-// columns [i0, i1) of every packed row
-static void pack_cols_host(const int32_t* actions, uint32_t* packed, int64_t T, int64_t N, int64_t i0, int64_t i1) {
+// columns [i0, i1) of every packed row; mode 0 = scalar, 1 = SSE2, 2 = AVX2 (host_pack_mode)
+static void pack_cols_host(const int32_t* actions, uint32_t* packed, int64_t T, int64_t N, int64_t i0, int64_t i1,
+                           int mode) {
   const int64_t words = (T + 15) / 16;
-#if GU_HOST_SIMD
-  const char* force = getenv("GU_HOST_PACK");               // developer / test switch: "scalar", "sse2"
-  const bool scalar = force && force[0] == 's' && force[1] == 'c';
-  const bool avx2 = __builtin_cpu_supports("avx2") && !(force && force[0] == 's' && force[1] == 's');
-#endif
   for (int64_t w = 0; w < words; ++w) {
     uint32_t* out = packed + w * N;
     const int32_t* in = actions + w * 16 * N;
     const int steps = static_cast<int>(T - w * 16 < 16 ? T - w * 16 : 16);
 #if GU_HOST_SIMD
-    if (steps == 16 && !scalar) {
-      if (avx2) pack_row16_avx2(in, out, N, i0, i1);
+    if (steps == 16 && mode != 0) {
+      if (mode == 2) pack_row16_avx2(in, out, N, i0, i1);
       else pack_row16_sse2(in, out, N, i0, i1);
       continue;
     }
 #endif
     pack_row_scalar(in, out, N, steps, i0, i1);
   }
+}
+
+// decided once per call, before the worker threads start
+static int host_pack_mode() {
+#if GU_HOST_SIMD
+  const char* force = getenv("GU_HOST_PACK");               // developer / test switch: "scalar", "sse2"
+  if (force && force[0] == 's' && force[1] == 'c') return 0;
+  if (force && force[0] == 's' && force[1] == 's') return 1;
+  return __builtin_cpu_supports("avx2") ? 2 : 1;
+#else
+  return 0;
+#endif
 }
 }  // namespace gu
 
@@ -398,14 +406,15 @@ extern "C" __attribute__((visibility("default"))) int gu_pack_actions_host(const
   if (nt < 1) nt = 1;
   const int64_t chunks = (n_envs + 4095) / 4096;          // at least 16 KB of output per thread
   if (nt > chunks) nt = static_cast<int>(chunks);
+  const int mode = host_pack_mode();
   if (nt == 1) {
-    pack_cols_host(actions, packed, n_steps, n_envs, 0, n_envs);
+    pack_cols_host(actions, packed, n_steps, n_envs, 0, n_envs, mode);
     return GU_OK;
   }
   std::vector<std::thread> pool;
   for (int k = 0; k < nt; ++k) {
     const int64_t i0 = (n_envs * k / nt) & ~static_cast<int64_t>(15), i1 = k + 1 == nt ? n_envs : (n_envs * (k + 1) / nt) & ~static_cast<int64_t>(15);
-    pool.emplace_back(pack_cols_host, actions, packed, n_steps, n_envs, i0, i1);
+    pool.emplace_back(pack_cols_host, actions, packed, n_steps, n_envs, i0, i1, mode);
   }
   for (auto& t : pool) t.join();
   return GU_OK;
